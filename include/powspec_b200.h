@@ -1,0 +1,167 @@
+/*
+ * powspec_b200.h — C ABI of the B200-native replacement for powspec's hot path
+ * (mass assignment -> r2c FFT -> window-deconvolved multipole binning).
+ *
+ * Plain C: no CUDA / torch types in any signature.  Every entry point cites the
+ * reference interface it replaces (paths relative to cheng-zhao/powspec).
+ *
+ * Two layers are exported by libpowspec_b200.so:
+ *
+ *  1. the "psb_" API below: the same stages with plain structs, used by the
+ *     Python host mirror (powspec_b200/api.py), the tests and bench.py;
+ *  2. the five symbols of the reference's own seam (include/powspec_refabi.h):
+ *     genr_mesh, mesh_destroy, powspec, powspec_destroy, powspec_assign_names —
+ *     what the reference's unchanged C host links against instead of
+ *     genr_mesh.o / multipole.o.
+ *
+ * Error convention: functions returning pointers return NULL on
+ * failure, functions returning int return non-zero; a message in the reference's
+ * P_ERR style ("\n\x1B[31;1mError:\x1B[0m ...", src/define.h:102,129) is written
+ * to stderr and also kept for psb_last_error().  There is NO CPU fallback: if no
+ * CUDA device is usable every compute entry fails loudly.
+ */
+#ifndef POWSPEC_B200_H
+#define POWSPEC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSB_VERSION 1
+#define PSB_MAX_ELL 6           /* POWSPEC_MAX_ELL, src/define.h:94 */
+#define PSB_MAX_POLES 8
+
+/* particle assignment schemes: powspec_assign_t, src/genr_mesh.h:38-43 */
+enum { PSB_NGP = 0, PSB_CIC = 1, PSB_TSC = 2, PSB_PCS = 3 };
+
+/* A particle record is the reference's DATA {double x[3]; double w;}
+ * (src/read_cata.h:42-45): 4 doubles, 32 bytes, array of structures. */
+
+/* The members of CONF (src/load_conf.h:40-93) that genr_mesh() and powspec()
+ * read (src/genr_mesh.c:654-669,683,896-897; src/multipole.c:310-319,341-344),
+ * plus the two choices that are compile-time in the reference
+ * (-DSINGLE_PREC, Makefile:14) or absent (device). */
+typedef struct {
+  int ncat;             /* CONF.ndata: number of catalogues, 1 or 2            */
+  int issim;            /* CONF.issim   (CUBIC_SIM)                            */
+  int intlace;          /* CONF.intlace (GRID_INTERLACE)                       */
+  int assign;           /* CONF.assign  (PARTICLE_ASSIGN) PSB_NGP..PSB_PCS     */
+  int gsize;            /* CONF.gsize   (GRID_SIZE)                            */
+  int logscale;         /* CONF.logscale: kmin/kmax/kbin are then in log10     */
+  int verbose;          /* CONF.verbose: print the reference's progress lines  */
+  int npole;            /* CONF.npole                                          */
+  int poles[PSB_MAX_POLES];     /* CONF.poles: sorted, unique, 0..6            */
+  int has_bsize;        /* CONF.bsize != NULL                                  */
+  int isauto[2];        /* CONF.isauto                                         */
+  int iscross;          /* CONF.iscross                                        */
+  double los[3];        /* CONF.los   (LINE_OF_SIGHT, sims)                    */
+  double bsize[3];      /* CONF.bsize (BOX_SIZE)                               */
+  double bpad[3];       /* CONF.bpad  (BOX_PAD, surveys without BOX_SIZE)      */
+  double kmin, kmax, kbin;      /* CONF.kmin/kmax/kbin; kmax <= 0: unset       */
+  int precision;        /* sizeof mesh real: 8 (default build) or 4 (SINGLE_PREC) */
+  int device;           /* CUDA device ordinal                                  */
+} psb_params;
+
+/* Where the particle arrays live. */
+enum {
+  PSB_MEM_HOST = 0,     /* host memory (pageable or pinned; detected)          */
+  PSB_MEM_DEVICE = 1    /* already resident on `device` (bench "value" leg)    */
+};
+
+/* The members of CATA (src/read_cata.h:47-59) the path reads. */
+typedef struct {
+  const double *data[2];        /* CATA.data[i]: ndata[i] x {x,y,z,w}          */
+  const double *rand[2];        /* CATA.rand[i] (surveys)                      */
+  size_t ndata[2], nrand[2];
+  double wdata[2], wrand[2];    /* CATA.wdata / wrand                          */
+  double alpha[2];              /* CATA.alpha (surveys, from read_cata)        */
+  double shot[2], norm[2];      /* surveys: inputs; sims: computed by the path
+                                   (src/genr_mesh.c:904-909)                   */
+  int memspace;                 /* PSB_MEM_HOST / PSB_MEM_DEVICE               */
+} psb_cats;
+
+typedef struct psb_context psb_context;         /* device, stream, buffers, FFT plans */
+typedef struct psb_result psb_result;           /* what PK + MESH metadata carry       */
+
+/* Context: owns the CUDA stream, mesh buffers, cuFFT plans and scratch for one
+ * device; buffers are grown on demand and reused across runs.  Replaces
+ * mesh_init / mesh_destroy (src/genr_mesh.c:650-747, 615-640) and the FFTW plan
+ * handling of src/fftw_define.h:32-64.  Returns NULL if no CUDA device. */
+psb_context *psb_create(int device);
+void psb_destroy(psb_context *ctx);
+
+/* The whole replaced span: genr_mesh() (src/genr_mesh.c:874-926) followed by
+ * powspec() (src/multipole.c:1179-1278).  The particle arrays are only read. */
+psb_result *psb_run(psb_context *ctx, const psb_params *par, const psb_cats *cats);
+
+/* Stage-level entry points (the same work in two calls, as the reference's
+ * main() makes them, src/powspec.c:47,55).  psb_mesh leaves the density meshes
+ * on the device inside ctx; psb_power consumes them. */
+int psb_mesh(psb_context *ctx, const psb_params *par, const psb_cats *cats);
+psb_result *psb_power(psb_context *ctx, const psb_params *par);
+
+void psb_result_free(psb_result *res);
+
+/* Result accessors (PK members, src/multipole.h:38-61; MESH metadata,
+ * src/genr_mesh.h:48-70; CATA.shot/norm). */
+enum {
+  PSB_GET_K = 0,        /* double[nbin]      PK.k                              */
+  PSB_GET_KEDGE,        /* double[nbin+1]    PK.kedge                          */
+  PSB_GET_KM,           /* double[nbin]      PK.km                             */
+  PSB_GET_CNT,          /* uint64[nbin]      PK.cnt                            */
+  PSB_GET_LCNT,         /* double[nl*nbin]   PK.lcnt (sims)                    */
+  PSB_GET_PL,           /* double[nl*nbin]   PK.pl[idx]                        */
+  PSB_GET_XPL,          /* double[nl*nbin]   PK.xpl                            */
+  PSB_GET_SHOT,         /* double[2]         CATA.shot                         */
+  PSB_GET_NORM,         /* double[2]         CATA.norm                         */
+  PSB_GET_BMIN,         /* double[3]         MESH.min                          */
+  PSB_GET_BSIZE,        /* double[3]         MESH.bsize                        */
+  PSB_GET_BMAX          /* double[3]         MESH.max                          */
+};
+int psb_result_nbin(const psb_result *res);
+int psb_result_nl(const psb_result *res);
+/* copies into dst, returns the element count or -1 if absent */
+long psb_result_get(const psb_result *res, int what, int idx, void *dst);
+
+/* Copy a density mesh out of the context (tests): field 0 = Fr, 1 = Frl (the
+ * half-cell shifted one), catalogue `cat`; dst holds gsize^3 reals of the
+ * run's precision, unpadded, z fastest (IDX, src/define.h:134).  Only valid
+ * between psb_mesh and psb_power. */
+int psb_copy_mesh(psb_context *ctx, int cat, int field, void *dst);
+
+/* Box defined by the last psb_mesh (def_box, src/genr_mesh.c:509-578): MESH.min,
+ * MESH.bsize, MESH.max. */
+int psb_mesh_box(const psb_context *ctx, double bmin[3], double bsize[3], double bmax[3]);
+
+/* Device timings of the last run, in milliseconds, measured with CUDA events on
+ * the context's stream.  Index with PSB_T_*. */
+enum {
+  PSB_T_H2D = 0, PSB_T_BOUNDS, PSB_T_SORT, PSB_T_MEMSET, PSB_T_ASSIGN,
+  PSB_T_FFT, PSB_T_GEOM, PSB_T_BIN, PSB_T_YLM, PSB_T_TOTAL, PSB_T_COUNT
+};
+int psb_timings(const psb_context *ctx, double *ms, int n);
+/* number of kernel launches (ours + cuFFT calls counted as 1) of the last run */
+long psb_launch_count(const psb_context *ctx);
+
+/* Tunables (tests / ablations): name = "sort" (0/1), "geom_cache" (0/1) ... */
+int psb_set_option(psb_context *ctx, const char *name, long value);
+
+const char *psb_last_error(void);
+int psb_device_count(void);
+
+/* Device-side synthetic catalogue generator for benchmarks:
+ * fills n x {x,y,z,w} on the device; kind 0 = uniform in [0,L)^3, 1 = clustered.
+ * Returns a device pointer to be released with psb_device_free. */
+double *psb_generate_catalog(psb_context *ctx, size_t n, double boxsize, int kind,
+    uint64_t seed);
+void psb_device_free(psb_context *ctx, void *ptr);
+/* copy device catalogue to host (tests) */
+int psb_copy_to_host(psb_context *ctx, void *dst, const void *src_dev, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

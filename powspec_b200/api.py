@@ -1,0 +1,434 @@
+"""Python host mirror of the reference's operator interface for the hot path.
+
+Names and argument meaning follow the reference's C entry points
+(cheng-zhao/powspec):
+
+    genr_mesh(conf, cata)        src/genr_mesh.h:86   -> Mesh
+    powspec(conf, cata, mesh)    src/multipole.h:78   -> PK
+    mesh_destroy(mesh)           src/genr_mesh.h:94
+    powspec_destroy(pk)          src/multipole.h:86
+    powspec_assign_names         src/genr_mesh.h:45
+
+``Conf`` carries the members of CONF that the two stages read
+(src/load_conf.h:40-93), ``Cata`` the members of CATA (src/read_cata.h:47-59),
+``PK`` the members of PK the host reads back (src/multipole.h:38-61).  Errors:
+the C layer prints the reference's P_ERR-style message and returns NULL; here
+that becomes ``PowspecB200Error`` (the reference's main() maps it to
+POWSPEC_ERR_MESH / POWSPEC_ERR_PK, src/powspec.c:47-60).
+
+Everything numerical happens in ``libpowspec_b200.so``; this file only marshals
+pointers.  PyTorch is optional here and only used to hand over device pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+powspec_assign_names = ["NGP", "CIC", "TSC", "PCS"]
+
+POWSPEC_ERR_MESH = -13      # src/define.h:122
+POWSPEC_ERR_PK = -14        # src/define.h:123
+
+(T_H2D, T_BOUNDS, T_SORT, T_MEMSET, T_ASSIGN, T_FFT, T_GEOM, T_BIN, T_YLM, T_TOTAL,
+ T_COUNT) = range(11)
+TIMING_NAMES = ["h2d", "bounds", "sort", "memset", "assign", "fft", "geom", "bin", "ylm", "total"]
+
+(GET_K, GET_KEDGE, GET_KM, GET_CNT, GET_LCNT, GET_PL, GET_XPL, GET_SHOT, GET_NORM,
+ GET_BMIN, GET_BSIZE, GET_BMAX) = range(12)
+
+
+class PowspecB200Error(RuntimeError):
+    def __init__(self, msg, code=None):
+        super().__init__(msg)
+        self.code = code
+
+
+class _Params(C.Structure):
+    _fields_ = [
+        ("ncat", C.c_int), ("issim", C.c_int), ("intlace", C.c_int), ("assign", C.c_int),
+        ("gsize", C.c_int), ("logscale", C.c_int), ("verbose", C.c_int), ("npole", C.c_int),
+        ("poles", C.c_int * 8), ("has_bsize", C.c_int), ("isauto", C.c_int * 2),
+        ("iscross", C.c_int), ("los", C.c_double * 3), ("bsize", C.c_double * 3),
+        ("bpad", C.c_double * 3), ("kmin", C.c_double), ("kmax", C.c_double),
+        ("kbin", C.c_double), ("precision", C.c_int), ("device", C.c_int),
+    ]
+
+
+class _Cats(C.Structure):
+    _fields_ = [
+        ("data", C.c_void_p * 2), ("rand", C.c_void_p * 2),
+        ("ndata", C.c_size_t * 2), ("nrand", C.c_size_t * 2),
+        ("wdata", C.c_double * 2), ("wrand", C.c_double * 2), ("alpha", C.c_double * 2),
+        ("shot", C.c_double * 2), ("norm", C.c_double * 2), ("memspace", C.c_int),
+    ]
+
+
+_lib = None
+
+
+def library_path() -> str:
+    return os.path.join(HERE, "libpowspec_b200.so")
+
+
+def load_library():
+    """dlopen libpowspec_b200.so (built in-tree by powspec_b200/build.py).
+    Fails loudly if it is missing: there is no fallback implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise PowspecB200Error(
+            f"{path} is missing: build it with `python -m powspec_b200.build` "
+            "(nvcc, sm_100a). powspec_b200 has no CPU fallback.")
+    L = C.CDLL(path)
+    L.psb_last_error.restype = C.c_char_p
+    L.psb_device_count.restype = C.c_int
+    L.psb_create.restype = C.c_void_p
+    L.psb_create.argtypes = [C.c_int]
+    L.psb_destroy.argtypes = [C.c_void_p]
+    L.psb_run.restype = C.c_void_p
+    L.psb_run.argtypes = [C.c_void_p, C.POINTER(_Params), C.POINTER(_Cats)]
+    L.psb_mesh.restype = C.c_int
+    L.psb_mesh.argtypes = [C.c_void_p, C.POINTER(_Params), C.POINTER(_Cats)]
+    L.psb_power.restype = C.c_void_p
+    L.psb_power.argtypes = [C.c_void_p, C.POINTER(_Params)]
+    L.psb_result_free.argtypes = [C.c_void_p]
+    L.psb_result_nbin.argtypes = [C.c_void_p]
+    L.psb_result_nl.argtypes = [C.c_void_p]
+    L.psb_result_get.restype = C.c_long
+    L.psb_result_get.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.psb_copy_mesh.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    L.psb_mesh_box.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.psb_timings.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.psb_launch_count.restype = C.c_long
+    L.psb_launch_count.argtypes = [C.c_void_p]
+    L.psb_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_long]
+    L.psb_generate_catalog.restype = C.c_void_p
+    L.psb_generate_catalog.argtypes = [C.c_void_p, C.c_size_t, C.c_double, C.c_int, C.c_uint64]
+    L.psb_device_free.argtypes = [C.c_void_p, C.c_void_p]
+    L.psb_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    _lib = L
+    return L
+
+
+def _err(L, what, code=None):
+    msg = L.psb_last_error().decode(errors="replace").strip()
+    return PowspecB200Error(f"{what}: {msg}" if msg else what, code)
+
+
+# ---------------------------------------------------------------------------
+# the reference's data structures, host side
+# ---------------------------------------------------------------------------
+@dataclass
+class Conf:
+    """Members of CONF read by genr_mesh() and powspec() (src/load_conf.h:40-93)."""
+    ndata: int = 1                  # number of catalogues
+    issim: bool = True              # CUBIC_SIM
+    los: tuple = (0.0, 0.0, 1.0)    # LINE_OF_SIGHT
+    bsize: tuple | None = None      # BOX_SIZE (3 values) or None
+    bpad: tuple = (0.02, 0.02, 0.02)    # BOX_PAD
+    gsize: int = 256                # GRID_SIZE
+    assign: int = 2                 # PARTICLE_ASSIGN (index into powspec_assign_names)
+    intlace: bool = False           # GRID_INTERLACE
+    poles: tuple = (0, 2, 4)        # MULTIPOLE (sorted, unique)
+    kmin: float = 0.0               # KMIN (log10 of it for LOG_SCALE, src/load_conf.c:1352-1355)
+    kmax: float = -1.0              # KMAX; <= 0: unset (src/define.h:67-68)
+    logscale: bool = False          # LOG_SCALE
+    kbin: float = 0.01              # BIN_SIZE
+    isauto: tuple = (True, False)
+    iscross: bool = False
+    verbose: bool = False
+    # not in the reference's CONF: compile-time -DSINGLE_PREC there
+    precision: int = 8
+    device: int = 0
+
+    def _c(self) -> _Params:
+        p = _Params()
+        p.ncat = self.ndata
+        p.issim, p.intlace, p.assign = int(self.issim), int(self.intlace), int(self.assign)
+        p.gsize, p.logscale, p.verbose = int(self.gsize), int(self.logscale), int(self.verbose)
+        poles = list(self.poles)
+        p.npole = len(poles)
+        for i, v in enumerate(poles[:8]):
+            p.poles[i] = int(v)
+        p.has_bsize = int(self.bsize is not None)
+        if self.bsize is not None:
+            b = np.broadcast_to(np.asarray(self.bsize, dtype=np.float64), (3,))
+            for i in range(3):
+                p.bsize[i] = float(b[i])
+        for i in range(3):
+            p.los[i] = float(self.los[i])
+            p.bpad[i] = float(self.bpad[i])
+        p.isauto[0], p.isauto[1] = int(self.isauto[0]), int(self.isauto[1])
+        p.iscross = int(self.iscross)
+        p.kmin, p.kmax, p.kbin = float(self.kmin), float(self.kmax), float(self.kbin)
+        p.precision, p.device = int(self.precision), int(self.device)
+        return p
+
+
+@dataclass
+class Cata:
+    """CATA (src/read_cata.h:47-59).  ``data`` / ``rand``: per catalogue an
+    (N, 4) float64 array of DATA records {x, y, z, w}: a numpy array (host), or
+    a torch CUDA tensor / (device_ptr, n) pair (already resident in HBM)."""
+    data: list
+    rand: list | None = None
+    wdata: list | None = None
+    wrand: list | None = None
+    alpha: list | None = None
+    shot: list | None = None
+    norm: list | None = None
+
+    @property
+    def num(self):
+        return len(self.data)
+
+
+@dataclass
+class Mesh:
+    """MESH metadata (src/genr_mesh.h:48-70); the fields stay on the device."""
+    ctx: "Context"
+    Ng: int
+    min: np.ndarray
+    max: np.ndarray
+    bsize: np.ndarray
+    issim: bool
+    intlace: bool
+    assign: int
+    num: int
+
+    def field(self, cat=0, shifted=False) -> np.ndarray:
+        """Copy of Fr (or Frl, the half-cell shifted field) as (Ng,Ng,Ng)."""
+        return self.ctx.copy_mesh(cat, int(shifted))
+
+
+@dataclass
+class PK:
+    """PK (src/multipole.h:38-61) as the host reads it back (src/save_res.c:100-124)."""
+    nl: int
+    nbin: int
+    poles: list
+    k: np.ndarray
+    kedge: np.ndarray
+    km: np.ndarray
+    cnt: np.ndarray
+    lcnt: np.ndarray
+    pl: list
+    xpl: np.ndarray | None
+    shot: np.ndarray
+    norm: np.ndarray
+    timings_ms: dict = field(default_factory=dict)
+    launches: int = 0
+
+
+def _ptr_of(arr):
+    """(pointer, n, memspace, keepalive) of one particle array."""
+    if arr is None:
+        return 0, 0, 0, None
+    if isinstance(arr, tuple):          # (device pointer, n)
+        return int(arr[0]), int(arr[1]), 1, None
+    if hasattr(arr, "data_ptr"):        # torch tensor
+        t = arr
+        assert t.dim() == 2 and t.shape[1] == 4 and str(t.dtype) == "torch.float64"
+        t = t.contiguous()
+        return t.data_ptr(), t.shape[0], (1 if t.is_cuda else 0), t
+    a = np.ascontiguousarray(arr, dtype=np.float64)
+    assert a.ndim == 2 and a.shape[1] == 4, "particles must be (N, 4) {x,y,z,w}"
+    return a.ctypes.data, a.shape[0], 0, a
+
+
+class Context:
+    """psb_context: CUDA stream, mesh buffers, cuFFT plans (include/powspec_b200.h)."""
+
+    def __init__(self, device: int = 0):
+        self.L = load_library()
+        self.device = device
+        self.h = self.L.psb_create(device)
+        if not self.h:
+            raise _err(self.L, "psb_create", POWSPEC_ERR_MESH)
+        self._conf = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.psb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, name: str, value: int):
+        if self.L.psb_set_option(self.h, name.encode(), int(value)):
+            raise _err(self.L, "psb_set_option")
+
+    # -- genr_mesh
+    def genr_mesh(self, conf: Conf, cata: Cata) -> Mesh:
+        p = conf._c()
+        cats = _Cats()
+        keep = []
+        spaces = set()
+        for i in range(cata.num):
+            ptr, n, sp, ka = _ptr_of(cata.data[i])
+            keep.append(ka)
+            spaces.add(sp)
+            cats.data[i], cats.ndata[i] = ptr, n
+            if cata.wdata is not None:
+                cats.wdata[i] = float(cata.wdata[i])
+            elif sp == 0:
+                cats.wdata[i] = float(np.sum(np.asarray(cata.data[i])[:, 3]))
+            else:
+                raise PowspecB200Error("Cata.wdata is required for device-resident catalogues")
+            if not conf.issim:
+                ptr, n, sp, ka = _ptr_of(cata.rand[i])
+                keep.append(ka)
+                spaces.add(sp)
+                cats.rand[i], cats.nrand[i] = ptr, n
+                cats.wrand[i] = float(cata.wrand[i])
+                cats.alpha[i] = float(cata.alpha[i])
+                cats.shot[i] = float(cata.shot[i])
+                cats.norm[i] = float(cata.norm[i])
+        if len(spaces) != 1:
+            raise PowspecB200Error("all catalogues must live in the same memory space")
+        cats.memspace = spaces.pop()
+        if self.L.psb_mesh(self.h, C.byref(p), C.byref(cats)):
+            raise _err(self.L, "genr_mesh", POWSPEC_ERR_MESH)
+        bmin, bsize, bmax = np.zeros(3), np.zeros(3), np.zeros(3)
+        self.L.psb_mesh_box(self.h, bmin.ctypes.data, bsize.ctypes.data, bmax.ctypes.data)
+        self._conf = conf
+        return Mesh(ctx=self, Ng=conf.gsize, min=bmin, max=bmax, bsize=bsize, issim=conf.issim,
+                    intlace=conf.intlace, assign=conf.assign, num=cata.num)
+
+    def copy_mesh(self, cat: int, fld: int) -> np.ndarray:
+        conf = self._conf
+        ng = conf.gsize
+        out = np.empty((ng, ng, ng), dtype=np.float64 if conf.precision == 8 else np.float32)
+        if self.L.psb_copy_mesh(self.h, cat, fld, out.ctypes.data):
+            raise _err(self.L, "psb_copy_mesh")
+        return out
+
+    # -- powspec
+    def powspec(self, conf: Conf, cata: Cata | None, mesh: Mesh) -> PK:
+        p = conf._c()
+        r = self.L.psb_power(self.h, C.byref(p))
+        if not r:
+            raise _err(self.L, "powspec", POWSPEC_ERR_PK)
+        try:
+            L = self.L
+            nbin, nl = L.psb_result_nbin(r), L.psb_result_nl(r)
+
+            def get(what, n, dtype=np.float64, idx=0):
+                a = np.empty(n, dtype=dtype)
+                return a if L.psb_result_get(r, what, idx, a.ctypes.data) >= 0 else None
+
+            pl = []
+            for i in range(2):
+                q = get(GET_PL, nl * nbin, idx=i)
+                pl.append(None if q is None else q.reshape(nl, nbin))
+            x = get(GET_XPL, nl * nbin)
+            pk = PK(nl=nl, nbin=nbin, poles=list(conf.poles), k=get(GET_K, nbin),
+                    kedge=get(GET_KEDGE, nbin + 1), km=get(GET_KM, nbin),
+                    cnt=get(GET_CNT, nbin, np.uint64), lcnt=get(GET_LCNT, nl * nbin).reshape(nl, nbin),
+                    pl=pl, xpl=None if x is None else x.reshape(nl, nbin),
+                    shot=get(GET_SHOT, 2), norm=get(GET_NORM, 2))
+            pk.timings_ms = self.timings()
+            pk.launches = int(L.psb_launch_count(self.h))
+            return pk
+        finally:
+            self.L.psb_result_free(r)
+
+    def timings(self) -> dict:
+        ms = (C.c_double * T_COUNT)()
+        self.L.psb_timings(self.h, ms, T_COUNT)
+        return {TIMING_NAMES[i]: ms[i] for i in range(T_COUNT - 1)}
+
+    # -- synthetic catalogues on the device
+    def generate_catalog(self, n: int, boxsize: float, kind: int = 0, seed: int = 1):
+        ptr = self.L.psb_generate_catalog(self.h, n, float(boxsize), int(kind), int(seed))
+        if not ptr:
+            raise _err(self.L, "psb_generate_catalog")
+        return (ptr, n)
+
+    def free_catalog(self, cat):
+        self.L.psb_device_free(self.h, cat[0])
+
+    def catalog_to_host(self, cat) -> np.ndarray:
+        out = np.empty((cat[1], 4), dtype=np.float64)
+        if self.L.psb_copy_to_host(self.h, out.ctypes.data, cat[0], out.nbytes):
+            raise _err(self.L, "psb_copy_to_host")
+        return out
+
+
+# ---------------------------------------------------------------------------
+# module-level functions with the reference's names
+# ---------------------------------------------------------------------------
+_default_ctx: dict = {}
+
+
+def _ctx_for(device: int) -> Context:
+    if device not in _default_ctx:
+        _default_ctx[device] = Context(device)
+    return _default_ctx[device]
+
+
+def genr_mesh(conf: Conf, cata: Cata) -> Mesh:
+    return _ctx_for(conf.device).genr_mesh(conf, cata)
+
+
+def powspec(conf: Conf, cata: Cata | None, mesh: Mesh) -> PK:
+    return mesh.ctx.powspec(conf, cata, mesh)
+
+
+def mesh_destroy(mesh: Mesh | None):
+    """Releases nothing on its own: buffers belong to the context and are reused."""
+    return None
+
+
+def powspec_destroy(pk: PK | None):
+    return None
+
+
+def run(data, *, ng, assign="TSC", interlace=False, poles=(0, 2, 4), box=None, issim=True,
+        rand=None, los=(0.0, 0.0, 1.0), kmin=0.0, kmax=-1.0, kbin=0.01, logscale=False,
+        bpad=(0.02, 0.02, 0.02), isauto=None, iscross=None, scalars=None, precision=8,
+        device=0, verbose=False, ctx: Context | None = None, keep_mesh=False, wdata=None):
+    """Convenience wrapper with the same keywords as oracle.Oracle.run (tests)."""
+    datas = list(data) if isinstance(data, (list, tuple)) and not (
+        isinstance(data, tuple) and len(data) == 2 and isinstance(data[0], int)) else [data]
+    ncat = len(datas)
+    if isauto is None:
+        isauto = [True] * ncat + [False] * (2 - ncat)
+    if iscross is None:
+        iscross = ncat == 2
+    conf = Conf(ndata=ncat, issim=issim, los=tuple(los),
+                bsize=None if box is None else tuple(np.broadcast_to(np.asarray(box, float), (3,))),
+                bpad=tuple(bpad), gsize=ng,
+                assign=powspec_assign_names.index(assign) if isinstance(assign, str) else assign,
+                intlace=interlace, poles=tuple(sorted(set(poles))), kmin=kmin, kmax=kmax,
+                logscale=logscale, kbin=kbin, isauto=tuple(isauto), iscross=iscross,
+                verbose=verbose, precision=precision, device=device)
+    cata = Cata(data=datas, wdata=wdata)
+    if not issim:
+        rands = list(rand) if isinstance(rand, (list, tuple)) else [rand]
+        cata.rand = rands
+        cata.wdata = [s["wdata"] for s in scalars]
+        cata.wrand = [s["wrand"] for s in scalars]
+        cata.alpha = [s["alpha"] for s in scalars]
+        cata.shot = [s["shot"] for s in scalars]
+        cata.norm = [s["norm"] for s in scalars]
+    c = ctx or _ctx_for(device)
+    mesh = c.genr_mesh(conf, cata)
+    fields = None
+    if keep_mesh:
+        fields = ([mesh.field(i) for i in range(ncat)],
+                  [mesh.field(i, True) for i in range(ncat)] if interlace else [None] * ncat)
+    pk = c.powspec(conf, cata, mesh)
+    if keep_mesh:
+        pk.Fr, pk.Frl = fields
+    return pk

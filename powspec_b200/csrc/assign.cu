@@ -1,0 +1,295 @@
+// Mass assignment for sm_100a: coordinate bounds, row-key counting sort and the
+// NGP / CIC / TSC / PCS scatter, with the half-cell shifted (interlaced) field
+// produced in the same pass over the particles.
+//
+// Replaces the reference's OpenMP loops (paths relative to cheng-zhao/powspec):
+//   get_coord_bound   src/genr_mesh.c:427-492
+//   ngp/cic/tsc/pcs   src/genr_mesh.c:50-71, 84-130, 143-234, 247-412
+//   shift_cat         src/genr_mesh.c:590-602   (fused: per-particle wrap)
+//   gen_dens          src/genr_mesh.c:793-858   (orchestrated in context.cu)
+//
+// Design: particles are 32-byte records read once with
+// two 128-bit loads; a counting sort on the (x,y) row of the base cell makes
+// every warp work on one mesh row neighbourhood, so the read-modify-write
+// traffic of the fp64 reductions stays in L2 and each mesh sector goes to HBM
+// once.  Accumulation uses no-return global reductions (RED.ADD.F64/F32), which
+// on this part are faster than CAS-emulated fp64 shared-memory atomics.
+//
+// Arithmetic that decides an integer (the cell index) is spelled with
+// round-to-nearest intrinsics in the reference's operation order
+// ((x - origin) * Ng / L), so no FMA contraction can move a particle.
+
+#include "psb_internal.h"
+
+#include <cfloat>
+
+namespace psb {
+
+// ---------------------------------------------------------------------------
+// bounds: per-block partial min/max of the three coordinates
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_bounds(const double2 *__restrict__ p,
+    size_t n, double *__restrict__ partials) {
+  double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX};
+  double hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n;
+       i += (size_t) gridDim.x * blockDim.x) {
+    double2 a = __ldg(p + 2 * i), b = __ldg(p + 2 * i + 1);
+    lo[0] = fmin(lo[0], a.x); hi[0] = fmax(hi[0], a.x);
+    lo[1] = fmin(lo[1], a.y); hi[1] = fmax(hi[1], a.y);
+    lo[2] = fmin(lo[2], b.x); hi[2] = fmax(hi[2], b.x);
+  }
+  __shared__ double s[6][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      lo[a] = fmin(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+      hi[a] = fmax(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+    }
+    if (lane == 0) { s[a][warp] = lo[a]; s[3 + a][warp] = hi[a]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double v = s[threadIdx.x][0];
+    for (int w = 1; w < 8; w++)
+      v = (threadIdx.x < 3) ? fmin(v, s[threadIdx.x][w]) : fmax(v, s[threadIdx.x][w]);
+    partials[blockIdx.x * 6 + threadIdx.x] = v;
+  }
+}
+
+int launch_bounds(const double *p, size_t n, double *partials, int nblk,
+    cudaStream_t st) {
+  k_bounds<<<nblk, 256, 0, st>>>(reinterpret_cast<const double2 *>(p), n, partials);
+  PSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// grid coordinate and base cell, in the reference's operation order
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double grid_coord(double x, double org, double len, int ng) {
+  // (x - org) * Ng / L : src/genr_mesh.c:57,91,152,256
+  return __ddiv_rn(__dmul_rn(__dsub_rn(x, org), (double) ng), len);
+}
+
+__device__ __forceinline__ int base_cell(double t, int ng) {
+  int c = (int) t;
+  // quirk Q8: a coordinate that rounds to t == Ng indexes out
+  // of bounds in the reference; wrap it instead
+  if (c >= ng) c -= ng;
+  if (c < 0) c = 0;
+  return c;
+}
+
+// ---------------------------------------------------------------------------
+// counting sort by the (x,y) row of the base cell on the unshifted grid
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_row_keys(const double2 *__restrict__ p,
+    size_t n, AssignGeom g, uint32_t *__restrict__ keys, uint32_t *__restrict__ hist) {
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n;
+       i += (size_t) gridDim.x * blockDim.x) {
+    double2 a = __ldg(p + 2 * i);
+    int cx = base_cell(grid_coord(a.x, g.org[0], g.len[0], g.ng), g.ng);
+    int cy = base_cell(grid_coord(a.y, g.org[1], g.len[1], g.ng), g.ng);
+    uint32_t key = (uint32_t) cx * (uint32_t) g.ng + (uint32_t) cy;
+    keys[i] = key;
+    atomicAdd(hist + key, 1u);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_row_scatter(const double2 *__restrict__ p,
+    size_t n, const uint32_t *__restrict__ keys, uint32_t *__restrict__ cursor,
+    double2 *__restrict__ out) {
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n;
+       i += (size_t) gridDim.x * blockDim.x) {
+    double2 a = __ldg(p + 2 * i), b = __ldg(p + 2 * i + 1);
+    uint32_t pos = atomicAdd(cursor + keys[i], 1u);
+    out[2 * (size_t) pos] = a;
+    out[2 * (size_t) pos + 1] = b;
+  }
+}
+
+static int grid_for(size_t n, int per_block, int max_blocks) {
+  size_t b = (n + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > (size_t) max_blocks) b = max_blocks;
+  return (int) b;
+}
+
+int launch_row_keys(const double *p, size_t n, const AssignGeom &g, uint32_t *keys,
+    uint32_t *hist, cudaStream_t st) {
+  k_row_keys<<<grid_for(n, 256, 148 * 16), 256, 0, st>>>(
+      reinterpret_cast<const double2 *>(p), n, g, keys, hist);
+  PSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_row_scatter(const double *p, size_t n, const uint32_t *keys,
+    uint32_t *cursor, double *sorted, cudaStream_t st) {
+  k_row_scatter<<<grid_for(n, 256, 148 * 16), 256, 0, st>>>(
+      reinterpret_cast<const double2 *>(p), n, keys, cursor,
+      reinterpret_cast<double2 *>(sorted));
+  PSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// one axis of the assignment stencil: cells (periodic) and weights
+// ---------------------------------------------------------------------------
+template <int SCHEME> struct Stencil { static constexpr int N = SCHEME + 1; };
+
+__device__ __forceinline__ int wrap_up(int c, int ng) { return (c == ng - 1) ? 0 : c + 1; }
+__device__ __forceinline__ int wrap_dn(int c, int ng) { return (c == 0) ? ng - 1 : c - 1; }
+
+template <int SCHEME>
+__device__ __forceinline__ void axis_stencil(double t, int ng, int (&idx)[SCHEME + 1],
+    double (&w)[SCHEME + 1]) {
+  int c = (int) t;
+  double d = t - (double) c;    // exact
+  if (c >= ng) c -= ng;         // Q8 guard, see base_cell()
+  if (c < 0) c = 0;
+  if constexpr (SCHEME == 0) {  // NGP, src/genr_mesh.c:60-66
+    if (d >= 0.5) c = wrap_up(c, ng);
+    idx[0] = c; w[0] = 1.0;
+  }
+  else if constexpr (SCHEME == 1) {     // CIC, src/genr_mesh.c:98-108
+    idx[0] = c; idx[1] = wrap_up(c, ng);
+    w[1] = d; w[0] = 1.0 - d;
+  }
+  else if constexpr (SCHEME == 2) {     // TSC, src/genr_mesh.c:157-173
+    double h;
+    if (d < 0.5) {
+      idx[1] = c; idx[0] = wrap_dn(c, ng); idx[2] = wrap_up(c, ng);
+      h = 0.5 - d;
+    }
+    else {
+      idx[0] = c; idx[1] = wrap_up(c, ng); idx[2] = wrap_up(idx[1], ng);
+      d = 1.0 - d;
+      h = 0.5 + d;
+    }
+    w[0] = h * (h * 0.5);
+    w[1] = 0.75 - d * d;
+    w[2] = 1.0 - w[0] - w[1];
+  }
+  else {                                // PCS, src/genr_mesh.c:256-272 (units of 1/6)
+    idx[1] = c; idx[0] = wrap_dn(c, ng); idx[2] = wrap_up(c, ng);
+    idx[3] = wrap_up(idx[2], ng);
+    double d2 = d * d;
+    w[3] = d2 * d;
+    w[2] = 1.0 + 3.0 * (d + d2 - w[3]);
+    w[1] = 4.0 - 6.0 * d2 + 3.0 * w[3];
+    w[0] = 6.0 - w[1] - w[2] - w[3];
+  }
+}
+
+template <typename real> __device__ __forceinline__ void red_add(real *addr, double v) {
+  atomicAdd(addr, (real) v);    // result unused -> RED.E.ADD.F64 / .F32
+}
+
+template <int SCHEME, typename real>
+__device__ __forceinline__ void scatter_one(const double x[3], double pw,
+    const double org[3], const AssignGeom &g, real *__restrict__ mesh) {
+  constexpr int NS = SCHEME + 1;
+  int ix[NS], iy[NS], iz[NS];
+  double wx[NS], wy[NS], wz[NS];
+  axis_stencil<SCHEME>(grid_coord(x[0], org[0], g.len[0], g.ng), g.ng, ix, wx);
+  axis_stencil<SCHEME>(grid_coord(x[1], org[1], g.len[1], g.ng), g.ng, iy, wy);
+  axis_stencil<SCHEME>(grid_coord(x[2], org[2], g.len[2], g.ng), g.ng, iz, wz);
+  // the particle weight enters through the x weights (src/genr_mesh.c:110-111,
+  // 175-177); PCS folds 1/216 = 0x1.2f684bda12f68p-8 into it (:274-278)
+  if constexpr (SCHEME == 3) pw *= 0x1.2f684bda12f68p-8;
+#pragma unroll
+  for (int a = 0; a < NS; a++) wx[a] *= pw;
+#pragma unroll
+  for (int a = 0; a < NS; a++) {
+#pragma unroll
+    for (int b = 0; b < NS; b++) {
+      const double wxy = wx[a] * wy[b];
+      real *row = mesh + ((size_t) ix[a] * g.ng + iy[b]) * g.rowlen;
+#pragma unroll
+      for (int c = 0; c < NS; c++) red_add(row + iz[c], wxy * wz[c]);
+    }
+  }
+}
+
+template <int SCHEME, typename real, bool INTERLACE>
+__global__ void __launch_bounds__(256) k_assign(const double2 *__restrict__ p, size_t n,
+    AssignGeom g, double wscale, real *__restrict__ mesh0, real *__restrict__ mesh1) {
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n;
+       i += (size_t) gridDim.x * blockDim.x) {
+    double2 a = __ldg(p + 2 * i), b = __ldg(p + 2 * i + 1);
+    double x[3] = {a.x, a.y, b.x};
+    const double pw = b.y * wscale;
+    scatter_one<SCHEME, real>(x, pw, g.org, g, mesh0);
+    if constexpr (INTERLACE) {
+      // shift_cat, src/genr_mesh.c:595-600: periodic wrap into the shifted box
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+        if (x[k] >= __dadd_rn(g.sorg[k], g.len[k])) x[k] = __dsub_rn(x[k], g.len[k]);
+      scatter_one<SCHEME, real>(x, pw, g.sorg, g, mesh1);
+    }
+  }
+}
+
+template <int SCHEME, typename real>
+static int launch_assign_t(const double *p, size_t n, const AssignGeom &g, double wscale,
+    void *m0, void *m1, cudaStream_t st) {
+  const int grid = grid_for(n, 256, 148 * 32);
+  const double2 *pp = reinterpret_cast<const double2 *>(p);
+  if (m1)
+    k_assign<SCHEME, real, true><<<grid, 256, 0, st>>>(pp, n, g, wscale,
+        static_cast<real *>(m0), static_cast<real *>(m1));
+  else
+    k_assign<SCHEME, real, false><<<grid, 256, 0, st>>>(pp, n, g, wscale,
+        static_cast<real *>(m0), nullptr);
+  PSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_assign(const double *p, size_t n, const AssignGeom &g, int scheme,
+    int precision, double wscale, void *mesh0, void *mesh1, cudaStream_t st) {
+  if (n == 0) return 0;
+#define PSB_DISPATCH(S)                                                         \
+  case S:                                                                       \
+    return precision == 8                                                       \
+        ? launch_assign_t<S, double>(p, n, g, wscale, mesh0, mesh1, st)         \
+        : launch_assign_t<S, float>(p, n, g, wscale, mesh0, mesh1, st);
+  switch (scheme) {
+    PSB_DISPATCH(0)
+    PSB_DISPATCH(1)
+    PSB_DISPATCH(2)
+    PSB_DISPATCH(3)
+    default:
+      set_error("unrecognised particle assignment scheme: %d\n", scheme);
+      return -1;
+  }
+#undef PSB_DISPATCH
+}
+
+// ---------------------------------------------------------------------------
+// padded (in-place FFT layout) -> dense copy, for tests
+// ---------------------------------------------------------------------------
+template <typename real>
+__global__ void k_unpad(const real *__restrict__ src, real *__restrict__ dst, int ng,
+    int rowlen) {
+  const size_t nrow = (size_t) ng * ng;
+  for (size_t r = blockIdx.x; r < nrow; r += gridDim.x)
+    for (int k = threadIdx.x; k < ng; k += blockDim.x)
+      dst[r * ng + k] = src[r * rowlen + k];
+}
+
+int launch_unpad_copy(const void *mesh, void *dst, int ng, int rowlen, int precision,
+    cudaStream_t st) {
+  if (precision == 8)
+    k_unpad<double><<<148 * 8, 128, 0, st>>>(static_cast<const double *>(mesh),
+        static_cast<double *>(dst), ng, rowlen);
+  else
+    k_unpad<float><<<148 * 8, 128, 0, st>>>(static_cast<const float *>(mesh),
+        static_cast<float *>(dst), ng, rowlen);
+  PSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace psb

@@ -1,0 +1,514 @@
+// Fourier-space stage for sm_100a: mode counting, the fused
+// interlace-combine + window correction + mu / L_ell(mu) + per-bin reduction
+// kernel, and the real-spherical-harmonic passes of the survey estimator.
+//
+// Replaces the reference's OpenMP loops (paths relative to cheng-zhao/powspec):
+//   powspec_precomp          src/multipole.c:111-257   (k_spectrum<GEOM>)
+//   interlace combine        src/multipole.c:462-487   (fused, or k_combine)
+//   count_mode_sim_lin/_log  src/multipole.c:778-898, 911-1031 (k_spectrum<SIM>)
+//   count_mode_lin/_log      src/multipole.c:579-660, 673-754  (k_spectrum<SURVEY>)
+//   dens_k<ell>              src/mp_template.c:48-149  (k_ylm_weight_r, k_ylm_accum_k)
+//   legpoly / YlmR_l<ell>    math/legpoly.h:47-61, math/spherical.h:54-260
+//
+// Design: the reference materialises an `alias` array of Ncmplx
+// reals and reads it back in every pass; here the window factor is the product
+// of three per-axis tables (computed on the host with libm, quirk Q1 included)
+// and the "cell in range" flag is re-derived from the same IEEE operations, so a
+// pass reads each complex cell exactly once and writes nothing but nl*nbin sums.
+// One warp owns one (i,j) row of the half spectrum; along the row |k| is
+// monotone, so lanes with equal bin index are contiguous and a segmented warp
+// scan leaves one add per (bin, warp-row) into warp-private shared-memory bins —
+// no atomics, deterministic order.  Block partials are reduced by a second tiny
+// kernel in fixed order.
+
+#include "psb_internal.h"
+
+namespace psb {
+
+namespace {
+
+enum { MODE_GEOM = 0, MODE_SIM = 1, MODE_SURVEY = 2 };
+
+template <typename real> struct C2;
+template <> struct C2<double> { using type = double2; };
+template <> struct C2<float> { using type = float2; };
+
+// math/legpoly.h:47-61
+__device__ __forceinline__ double legendre(int ell, double x) {
+  const double x2 = x * x;
+  switch (ell) {
+    case 0: return 1.0;
+    case 1: return x;
+    case 2: return 1.5 * x2 - 0.5;
+    case 3: return 2.5 * x * (x2 - 0.6);
+    case 4: return 4.375 * x2 * x2 - 3.75 * x2 + 0.375;
+    case 5: return 8.75 * x * (0.9 * x2 * x2 - x2 + 0x1.b6db6db6db6dbp-3);
+    case 6: return 14.4375 * x2 * x2 * x2 - 19.6875 * x2 * x2 + 6.5625 * x2 - 0.3125;
+    default: return 0.0;
+  }
+}
+
+// Bin of a squared wavenumber, exactly as the reference evaluates it
+// (src/multipole.c:145-159): returns -1 for cells it marks unused (alias = 0).
+__device__ __forceinline__ int bin_of(const BinGeom &g, double k2, double &kmod) {
+  kmod = __dsqrt_rn(k2);
+  if (!g.logk) {
+    if (kmod < g.k0 || kmod >= g.k1) return -1;
+    int b = (int) __ddiv_rn(__dsub_rn(kmod, g.k0), g.dk);
+    return (b < 0 || b >= g.nbin) ? -1 : b;
+  }
+  // log bins: glibc's log10 decides in the reference.  The host has bisected,
+  // with libm, the smallest k^2 that lands in each bin (monotone expression);
+  // the device only needs a guess and two comparisons.
+  const double *e = g.k2edge;
+  if (!(k2 >= e[0]) || k2 >= e[g.nbin]) return -1;
+  int b = (int) ((0.5 * log10(k2) - g.k0) / g.dk);
+  b = max(0, min(b, g.nbin - 1));
+  while (k2 < e[b]) b--;
+  while (k2 >= e[b + 1]) b++;
+  return b;
+}
+
+// Segmented inclusive scan over contiguous equal keys, then the last lane of
+// every segment adds its total into the warp's private bins.
+template <int NV>
+__device__ __forceinline__ void warp_bin_add(int key, double (&v)[NV], double *bins,
+    int nbin, int lane) {
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int kprev = __shfl_up_sync(0xffffffffu, key, off);
+    const bool take = (lane >= off) && (kprev == key);
+#pragma unroll
+    for (int q = 0; q < NV; q++) {
+      const double t = __shfl_up_sync(0xffffffffu, v[q], off);
+      if (take) v[q] += t;
+    }
+  }
+  const int knext = __shfl_down_sync(0xffffffffu, key, 1);
+  if (key >= 0 && (lane == 31 || knext != key)) {
+#pragma unroll
+    for (int q = 0; q < NV; q++) bins[q * nbin + key] += v[q];
+  }
+  __syncwarp();
+}
+
+template <typename real>
+__device__ __forceinline__ double2 ld_c(const void *base, size_t idx) {
+  using c2 = typename C2<real>::type;
+  c2 v = __ldg(reinterpret_cast<const c2 *>(base) + idx);
+  return make_double2((double) v.x, (double) v.y);
+}
+
+// MODE_GEOM : v = {cnt, km, lcnt[0..nl)}            NV = nl + 2
+// MODE_SIM  : v = {pl[0..nl)}                       NV = nl
+// MODE_SURVEY: v = {pl}                             NV = 1
+template <typename real, int NV, int MODE, bool INTERLACE>
+__global__ void __launch_bounds__(256) k_spectrum(BinGeom g, const void *__restrict__ Fa0,
+    const void *__restrict__ Fa1, const void *__restrict__ Fb0,
+    const void *__restrict__ Fb1, double *__restrict__ partials) {
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nwarp = blockDim.x >> 5;
+  const int nacc = NV * g.nbin;
+  double *bins = smem + (size_t) warp * nacc;
+  for (int q = lane; q < nacc; q += 32) bins[q] = 0.0;
+  __syncwarp();
+
+  const bool cross = (Fb0 != Fa0);
+  const size_t nrows = (size_t) g.nyloc * g.ng;
+  const size_t wstride = (size_t) gridDim.x * nwarp;
+  for (size_t row = (size_t) blockIdx.x * nwarp + warp; row < nrows; row += wstride) {
+    const int i = g.y0 + (int) (row / g.ng), j = (int) (row % g.ng);
+    const double ki = __ldg(g.kax[0] + i), kj = __ldg(g.kax[1] + j);
+    const double k2ij = __dadd_rn(__ldg(g.kax2[0] + i), __ldg(g.kax2[1] + j));
+    const double wij = __dmul_rn(__ldg(g.wax[0] + i), __ldg(g.wax[1] + j));
+    const double muij = __dadd_rn(__dmul_rn(ki, g.los[0]), __dmul_rn(kj, g.los[1]));
+    double pcij = 1.0, psij = 0.0;
+    if (INTERLACE) {
+      const double ci = __ldg(g.pc[0] + i), si = __ldg(g.ps[0] + i);
+      const double cj = __ldg(g.pc[1] + j), sj = __ldg(g.ps[1] + j);
+      pcij = ci * cj - si * sj;
+      psij = si * cj + ci * sj;
+    }
+    const size_t rbase = row * (size_t) g.ngk;
+    for (int kb = 0; kb < g.ngk; kb += 32) {
+      const int k = kb + lane;
+      int key = -1;
+      double v[NV];
+#pragma unroll
+      for (int q = 0; q < NV; q++) v[q] = 0.0;
+      if (k < g.ngk) {
+        double2 a0, a1, b0, b1;
+        if (MODE != MODE_GEOM) {
+          a0 = ld_c<real>(Fa0, rbase + k);
+          if (INTERLACE) a1 = ld_c<real>(Fa1, rbase + k);
+          if (cross) {
+            b0 = ld_c<real>(Fb0, rbase + k);
+            if (INTERLACE) b1 = ld_c<real>(Fb1, rbase + k);
+          }
+        }
+        const double k2 = __dadd_rn(k2ij, __ldg(g.kax2[2] + k));
+        double kmod;
+        key = bin_of(g, k2, kmod);
+        // sims skip the DC mode in the sums (src/multipole.c:806,939) but not
+        // in the counts (quirk Q3)
+        if (MODE == MODE_SIM && k2 == 0.0) key = -1;
+        if (key >= 0) {
+          const bool edge = (k == 0) || (((g.ng & 1) == 0) && k == (g.ng >> 1));
+          const double mult = edge ? 1.0 : 2.0;
+          double p = 0.0;
+          if (MODE != MODE_GEOM) {
+            if (INTERLACE) {
+              // delta = (F0 + e^{i s} F1) / 2, s = pi (n_i + n_j + k) / Ng
+              const double ck = __ldg(g.pc[2] + k), sk = __ldg(g.ps[2] + k);
+              const double c = pcij * ck - psij * sk, s = psij * ck + pcij * sk;
+              a0.x = 0.5 * (a0.x + c * a1.x - s * a1.y);
+              a0.y = 0.5 * (a0.y + s * a1.x + c * a1.y);
+              if (cross) {
+                b0.x = 0.5 * (b0.x + c * b1.x - s * b1.y);
+                b0.y = 0.5 * (b0.y + s * b1.x + c * b1.y);
+              }
+            }
+            if (!cross) b0 = a0;
+            const double alias = __dmul_rn(wij, __ldg(g.wax[2] + k));
+            p = (a0.x * b0.x + a0.y * b0.y) * alias * mult;
+          }
+          if (MODE == MODE_SURVEY) v[0] = p;
+          else {
+            const double mu = (k2 == 0.0) ? 0.0
+                : __ddiv_rn(__dadd_rn(muij, __dmul_rn(__ldg(g.kax[2] + k), g.los[2])), kmod);
+            constexpr int L0 = (MODE == MODE_GEOM) ? 2 : 0;
+            if (MODE == MODE_GEOM) {
+              v[0] = mult;
+              v[1] = mult * (g.logk ? 0.0 : kmod);
+            }
+#pragma unroll
+            for (int l = 0; l < NV - L0; l++) {
+              const int ell = g.poles[l];
+              // +mu / -mu half-planes cancel for odd ell (src/multipole.c:843-844):
+              // only the k = 0 and Nyquist planes contribute (quirk Q6)
+              if (!edge && (ell & 1)) continue;
+              const double leg = legendre(ell, mu);
+              // the DC mode has no direction: counted in cnt/km only
+              if (MODE == MODE_GEOM) v[L0 + l] = (k2 == 0.0) ? 0.0 : mult * leg;
+              else v[l] = p * leg;
+            }
+          }
+        }
+      }
+      warp_bin_add<NV>(key, v, bins, g.nbin, lane);
+    }
+  }
+  __syncthreads();
+  // block partial: sum the warps' bins in fixed order
+  double *out = partials + (size_t) blockIdx.x * nacc;
+  for (int q = threadIdx.x; q < nacc; q += blockDim.x) {
+    double s = 0.0;
+    for (int w = 0; w < nwarp; w++) s += smem[(size_t) w * nacc + q];
+    out[q] = s;
+  }
+}
+
+// out[q] += sum over blocks, in block order
+__global__ void k_reduce_partials(const double *__restrict__ partials, int nblk, int nacc,
+    double *__restrict__ out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nacc) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; b++) s += partials[(size_t) b * nacc + q];
+  out[q] += s;
+}
+
+__global__ void k_unpack_geometry(const double *__restrict__ acc, int nbin, int nl,
+    unsigned long long *__restrict__ cnt, double *__restrict__ km,
+    double *__restrict__ lcnt) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nbin) return;
+  cnt[b] = (unsigned long long) acc[b];         // exact: integer-valued sums < 2^53
+  km[b] = acc[nbin + b];
+  for (int l = 0; l < nl; l++) lcnt[l * nbin + b] = acc[(2 + l) * nbin + b];
+}
+
+struct LaunchShape { int blocks, threads; size_t smem; };
+
+template <typename K>
+int shape_for(K kernel, int nacc, LaunchShape &ls) {
+  // warp-private bins: nacc doubles per warp
+  int threads = 256;
+  size_t smem = (size_t) nacc * sizeof(double) * (threads / 32);
+  while (smem > 200 * 1024 && threads > 32) {
+    threads >>= 1;
+    smem = (size_t) nacc * sizeof(double) * (threads / 32);
+  }
+  if (smem > 200 * 1024) {
+    set_error("too many (multipole x k-bin) accumulators for the binning kernel: %d\n", nacc);
+    return -1;
+  }
+  PSB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      (int) smem));
+  int per_sm = 0;
+  PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+  if (per_sm < 1) per_sm = 1;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  ls.blocks = sms * per_sm;
+  ls.threads = threads;
+  ls.smem = smem;
+  return 0;
+}
+
+constexpr int MAX_BLOCKS = 148 * 8;
+
+template <typename real, int NV, int MODE, bool IL>
+int run_spectrum(const BinGeom &g, const void *Fa0, const void *Fa1, const void *Fb0,
+    const void *Fb1, double *out, double *scratch, size_t scratch_bytes, cudaStream_t st) {
+  auto kern = k_spectrum<real, NV, MODE, IL>;
+  const int nacc = NV * g.nbin;
+  LaunchShape ls;
+  if (shape_for(kern, nacc, ls)) return -1;
+  size_t rows = (size_t) g.nyloc * g.ng;
+  size_t need_blocks = (rows + ls.threads / 32 - 1) / (ls.threads / 32);
+  if ((size_t) ls.blocks > need_blocks) ls.blocks = (int) need_blocks;
+  if (ls.blocks > MAX_BLOCKS) ls.blocks = MAX_BLOCKS;
+  if ((size_t) ls.blocks * nacc * sizeof(double) > scratch_bytes) {
+    set_error("internal: binning scratch too small\n");
+    return -1;
+  }
+  kern<<<ls.blocks, ls.threads, ls.smem, st>>>(g, Fa0, Fa1, Fb0, Fb1, scratch);
+  PSB_CUDA(cudaGetLastError());
+  k_reduce_partials<<<(nacc + 127) / 128, 128, 0, st>>>(scratch, ls.blocks, nacc, out);
+  PSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+size_t bin_scratch_bytes(const BinGeom &g) {
+  // block partials plus one accumulator row for the geometry pass
+  return ((size_t) MAX_BLOCKS + 1) * (size_t) (g.nl + 2) * g.nbin * sizeof(double);
+}
+
+int launch_geometry(const BinGeom &g, unsigned long long *cnt, double *km, double *lcnt,
+    double *scratch, size_t scratch_bytes, cudaStream_t st) {
+  const int nl = g.issim ? g.nl : 0;
+  const int nacc = (nl + 2) * g.nbin;
+  double *acc = scratch;        // first nacc doubles: the reduced accumulators
+  double *part = scratch + nacc;
+  PSB_CUDA(cudaMemsetAsync(acc, 0, nacc * sizeof(double), st));
+  int rc = -1;
+  const size_t pb = scratch_bytes - nacc * sizeof(double);
+#define PSB_GEOM(NL)                                                            \
+  case NL:                                                                      \
+    rc = run_spectrum<double, NL + 2, MODE_GEOM, false>(g, nullptr, nullptr,    \
+        nullptr, nullptr, acc, part, pb, st);                                   \
+    break;
+  switch (nl) {
+    PSB_GEOM(0) PSB_GEOM(1) PSB_GEOM(2) PSB_GEOM(3) PSB_GEOM(4) PSB_GEOM(5)
+    PSB_GEOM(6) PSB_GEOM(7)
+    default: set_error("invalid number of multipoles: %d\n", nl); return -1;
+  }
+#undef PSB_GEOM
+  if (rc) return rc;
+  k_unpack_geometry<<<(g.nbin + 127) / 128, 128, 0, st>>>(acc, g.nbin, nl, cnt, km, lcnt);
+  PSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename real>
+static int launch_bin_t(const BinGeom &g, const void *Fa0, const void *Fa1, const void *Fb0,
+    const void *Fb1, double *pl, double *scratch, size_t sb, cudaStream_t st) {
+  const bool il = (Fa1 != nullptr);
+  if (!g.issim) {
+    return il ? run_spectrum<real, 1, MODE_SURVEY, true>(g, Fa0, Fa1, Fb0, Fb1, pl, scratch, sb, st)
+              : run_spectrum<real, 1, MODE_SURVEY, false>(g, Fa0, Fa1, Fb0, Fb1, pl, scratch, sb, st);
+  }
+#define PSB_SIM(NL)                                                             \
+  case NL:                                                                      \
+    return il ? run_spectrum<real, NL, MODE_SIM, true>(g, Fa0, Fa1, Fb0, Fb1, pl, scratch, sb, st)  \
+              : run_spectrum<real, NL, MODE_SIM, false>(g, Fa0, Fa1, Fb0, Fb1, pl, scratch, sb, st);
+  switch (g.nl) {
+    PSB_SIM(1) PSB_SIM(2) PSB_SIM(3) PSB_SIM(4) PSB_SIM(5) PSB_SIM(6) PSB_SIM(7)
+    default: set_error("invalid number of multipoles: %d\n", g.nl); return -1;
+  }
+#undef PSB_SIM
+}
+
+int launch_bin(const BinGeom &g, int precision, const void *Fa0, const void *Fa1,
+    const void *Fb0, const void *Fb1, double *pl, double *scratch, size_t scratch_bytes,
+    cudaStream_t st) {
+  return precision == 8
+      ? launch_bin_t<double>(g, Fa0, Fa1, Fb0, Fb1, pl, scratch, scratch_bytes, st)
+      : launch_bin_t<float>(g, Fa0, Fa1, Fb0, Fb1, pl, scratch, scratch_bytes, st);
+}
+
+// ---------------------------------------------------------------------------
+// in-place interlace combination (surveys: the combined field is reused)
+// ---------------------------------------------------------------------------
+template <typename real>
+__global__ void __launch_bounds__(256) k_combine(BinGeom g, typename C2<real>::type *F0,
+    const typename C2<real>::type *__restrict__ F1) {
+  using c2 = typename C2<real>::type;
+  const size_t nrows = (size_t) g.nyloc * g.ng;
+  for (size_t row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int i = g.y0 + (int) (row / g.ng), j = (int) (row % g.ng);
+    const double ci = g.pc[0][i], si = g.ps[0][i], cj = g.pc[1][j], sj = g.ps[1][j];
+    const double cij = ci * cj - si * sj, sij = si * cj + ci * sj;
+    for (int k = threadIdx.x; k < g.ngk; k += blockDim.x) {
+      const double ck = g.pc[2][k], sk = g.ps[2][k];
+      const double c = cij * ck - sij * sk, s = sij * ck + cij * sk;
+      const size_t idx = row * g.ngk + k;
+      c2 a = F0[idx], b = F1[idx];
+      c2 r;
+      r.x = (real) (0.5 * ((double) a.x + c * (double) b.x - s * (double) b.y));
+      r.y = (real) (0.5 * ((double) a.y + s * (double) b.x + c * (double) b.y));
+      F0[idx] = r;
+    }
+  }
+}
+
+int launch_combine(const BinGeom &g, int precision, void *F0, const void *F1,
+    cudaStream_t st) {
+  if (precision == 8)
+    k_combine<double><<<148 * 8, 256, 0, st>>>(g, static_cast<double2 *>(F0),
+        static_cast<const double2 *>(F1));
+  else
+    k_combine<float><<<148 * 8, 256, 0, st>>>(g, static_cast<float2 *>(F0),
+        static_cast<const float2 *>(F1));
+  PSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// real spherical harmonics (definition math/spherical.h:33-38), by recurrence:
+//   Y_lm = N_lm P_l^|m|(cos t) {cos(m p) | 1 | sin(|m| p)},  P without the
+//   Condon-Shortley phase, N_lm = sqrt((2l+1)/(4 pi) (l-|m|)!/(l+|m|)!) sqrt2^{m!=0}
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double ylm_real(int l, int m, double nrm, double cost,
+    double sint, double cosp, double sinp) {
+  const int am = m < 0 ? -m : m;
+  double cm = 1.0, sm = 0.0;
+  for (int k = 0; k < am; k++) {
+    const double c2 = cm * cosp - sm * sinp;
+    sm = sm * cosp + cm * sinp;
+    cm = c2;
+  }
+  double pmm = 1.0;
+  for (int k = 1; k <= am; k++) pmm *= (2 * k - 1) * sint;
+  double plm = pmm;
+  if (l > am) {
+    double pm1 = pmm, cur = (2 * am + 1) * cost * pmm;
+    for (int ll = am + 2; ll <= l; ll++) {
+      const double nxt = ((2 * ll - 1) * cost * cur - (ll + am - 1) * pm1) / (ll - am);
+      pm1 = cur; cur = nxt;
+    }
+    plm = cur;
+  }
+  return nrm * plm * (m > 0 ? cm : (m < 0 ? sm : 1.0));
+}
+
+static double ylm_norm(int l, int m) {
+  const int am = m < 0 ? -m : m;
+  double ratio = 1.0;
+  for (int k = l - am + 1; k <= l + am; k++) ratio /= k;
+  double nrm = sqrt((2 * l + 1) / (4 * 0x1.921fb54442d18p+1) * ratio);
+  if (am) nrm *= 0x1.6a09e667f3bcdp+0;
+  return nrm;
+}
+
+// out = Fr * Y_lm(r_hat), src/mp_template.c:65-95.  Both meshes padded (rowlen).
+template <typename real>
+__global__ void __launch_bounds__(256) k_ylm_weight_r(YlmGeom g, double nrm,
+    const real *__restrict__ Fr, real *__restrict__ out) {
+  const size_t nrows = (size_t) g.ng * g.ng;
+  for (size_t row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int i = (int) (row / g.ng), j = (int) (row % g.ng);
+    const double ri = (i + g.smin[0]) * g.bsize[0];
+    const double rj = (j + g.smin[1]) * g.bsize[1];
+    const double r2 = ri * ri + rj * rj;
+    const double rxy = sqrt(r2);
+    const real *src = Fr + row * g.rowlen;
+    real *dst = out + row * g.rowlen;
+    for (int k = threadIdx.x; k < g.ng; k += blockDim.x) {
+      if (row == 0) { dst[k] = src[k]; continue; }      // quirk Q5 (:75-78)
+      const double rk = (k + g.smin[2]) * g.bsize[2];
+      const double r3 = sqrt(r2 + rk * rk);
+      const double y = ylm_real(g.ell, g.m, nrm, rk / r3, rxy / r3, ri / rxy, rj / rxy);
+      dst[k] = (real) ((double) src[k] * y);
+    }
+  }
+}
+
+int launch_ylm_weight_r(const YlmGeom &g, int precision, const void *Fr, void *out,
+    cudaStream_t st) {
+  const double nrm = ylm_norm(g.ell, g.m);
+  if (precision == 8)
+    k_ylm_weight_r<double><<<148 * 8, 256, 0, st>>>(g, nrm,
+        static_cast<const double *>(Fr), static_cast<double *>(out));
+  else
+    k_ylm_weight_r<float><<<148 * 8, 256, 0, st>>>(g, nrm,
+        static_cast<const float *>(Fr), static_cast<float *>(out));
+  PSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Fkl += Fka * Y_lm(k_hat) on cells the reference marks used, src/mp_template.c:101-137
+template <typename real>
+__global__ void __launch_bounds__(256) k_ylm_accum_k(YlmGeom g, BinGeom bg, double nrm,
+    const typename C2<real>::type *__restrict__ Fka, typename C2<real>::type *Fkl) {
+  using c2 = typename C2<real>::type;
+  const size_t nrows = (size_t) g.ng * g.ng;
+  const double f0 = 1.0 / g.bsize[0], f1 = 1.0 / g.bsize[1], f2 = 1.0 / g.bsize[2];
+  for (size_t row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int i = (int) (row / g.ng), j = (int) (row % g.ng);
+    const double ki = f0 * ((i <= (g.ng >> 1)) ? i : i - g.ng);
+    const double kj = f1 * ((j <= (g.ng >> 1)) ? j : j - g.ng);
+    const double k2 = ki * ki + kj * kj;
+    const double k2ij = __dadd_rn(bg.kax2[0][i], bg.kax2[1][j]);
+    for (int k = threadIdx.x; k < g.ngk; k += blockDim.x) {
+      double kmod;
+      if (bin_of(bg, __dadd_rn(k2ij, bg.kax2[2][k]), kmod) < 0) continue;
+      const double kk = f2 * k;
+      const double k3 = sqrt(k2 + kk * kk);
+      double sh = 1.0;
+      if (k2 != 0.0 && k3 != 0.0) {
+        const double kxy = sqrt(k2);
+        sh = ylm_real(g.ell, g.m, nrm, kk / k3, kxy / k3, ki / kxy, kj / kxy);
+      }
+      const size_t idx = row * g.ngk + k;
+      c2 a = Fka[idx], acc = Fkl[idx];
+      acc.x = (real) ((double) acc.x + (double) a.x * sh);
+      acc.y = (real) ((double) acc.y + (double) a.y * sh);
+      Fkl[idx] = acc;
+    }
+  }
+}
+
+int launch_ylm_accum_k(const YlmGeom &g, const BinGeom &bg, int precision,
+    const void *Fka, void *Fkl, cudaStream_t st) {
+  const double nrm = ylm_norm(g.ell, g.m);
+  if (precision == 8)
+    k_ylm_accum_k<double><<<148 * 8, 256, 0, st>>>(g, bg, nrm,
+        static_cast<const double2 *>(Fka), static_cast<double2 *>(Fkl));
+  else
+    k_ylm_accum_k<float><<<148 * 8, 256, 0, st>>>(g, bg, nrm,
+        static_cast<const float2 *>(Fka), static_cast<float2 *>(Fkl));
+  PSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename real>
+__global__ void k_scale(real *m, size_t n, double f) {
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n;
+       i += (size_t) gridDim.x * blockDim.x)
+    m[i] = (real) ((double) m[i] * f);
+}
+
+int launch_scale(void *mesh, size_t n, double factor, int precision, cudaStream_t st) {
+  if (precision == 8) k_scale<double><<<148 * 16, 256, 0, st>>>((double *) mesh, n, factor);
+  else k_scale<float><<<148 * 16, 256, 0, st>>>((float *) mesh, n, factor);
+  PSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace psb

@@ -1,0 +1,1042 @@
+// Host orchestration and C ABI (include/powspec_b200.h) of the B200 hot path:
+// device buffers, cuFFT plans, the genr_mesh / powspec stage logic, result
+// normalisation.  Everything numerical runs in the kernels of assign.cu and
+// binning.cu or in cuFFT; what is computed on the host here is O(Ng) tables and
+// O(nl * nbin) normalisation, as in the reference.
+//
+// Reference map (paths relative to cheng-zhao/powspec):
+//   mesh_init / mesh_destroy   src/genr_mesh.c:650-747, 615-640 -> Context buffers
+//   def_box                    src/genr_mesh.c:509-578          -> define_box()
+//   gen_dens / genr_mesh       src/genr_mesh.c:793-858, 874-926 -> psb_mesh()
+//   FFTW plans / execution     src/fftw_define.h:32-64, src/multipole.c:444,459,493
+//                                                               -> cuFFT D2Z/Z2D in place
+//   powspec_init               src/multipole.c:306-421          -> init_bins()
+//   alias_corr                 src/multipole.c:46-100           -> window_axis() tables
+//   dens_k0, powspec, count_mode  src/multipole.c:435-505, 1179-1278, 1044-1162
+//                                                               -> psb_power()
+
+#include "psb_internal.h"
+#include "../../include/powspec_b200.h"
+
+#include <cufft.h>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace psb {
+
+// ---------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  // the reference's P_ERR format, src/define.h:102,129
+  fprintf(stderr, "\n\x1B[31;1mError:\x1B[0m %s", g_err);
+}
+const char *get_error() { return g_err; }
+
+static const double PI = 0x1.921fb54442d18p+1;  // src/define.h:37
+
+#define PSB_CUFFT(call)                                                         \
+  do {                                                                          \
+    cufftResult r_ = (call);                                                    \
+    if (r_ != CUFFT_SUCCESS) {                                                  \
+      psb::set_error("cuFFT failure %s at %s:%d: code %d\n", #call, __FILE__,   \
+          __LINE__, (int) r_);                                                  \
+      return -1;                                                                \
+    }                                                                           \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// growable device buffer
+// ---------------------------------------------------------------------------
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) {
+      set_error("failed to allocate %.3f GB of device memory: %s\n", bytes / 1e9,
+          cudaGetErrorString(e));
+      cudaGetLastError();
+      return -1;
+    }
+    cap = bytes;
+    return 0;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+
+struct Interval { int stage; cudaEvent_t a, b; };
+
+}  // namespace psb
+
+using namespace psb;
+
+// ---------------------------------------------------------------------------
+// the context
+// ---------------------------------------------------------------------------
+struct psb_context {
+  int device = 0;
+  int sms = 148;
+  cudaStream_t st = nullptr;            // compute
+  cudaStream_t st_geom = nullptr;       // data-independent mode counting
+  cudaEvent_t ev_geom = nullptr;
+
+  // particles
+  DevBuf part_in[2][2];                 // [cat][data|rand] staged copies of host arrays
+  DevBuf sorted, keys, hist, cursor, cubtmp, bounds_part;
+  void *pinned[2] = {nullptr, nullptr};
+  size_t pinned_bytes = 0;
+  cudaEvent_t pinned_free[2] = {nullptr, nullptr};
+
+  // meshes: [cat][field]; survey extras
+  DevBuf mesh[2][2];
+  DevBuf fkl[2], fka, fk0copy[2];
+
+  // FFT
+  cufftHandle plan_fwd = 0, plan_inv = 0;
+  int plan_ng = 0, plan_prec = 0;
+  bool have_fwd = false, have_inv = false;
+  DevBuf fftwork;
+
+  // tables and bins
+  DevBuf tables, binscratch, bins;
+  std::vector<double> host_tables;
+
+  // options
+  long opt_sort = 1;
+  long opt_sort_min = 1 << 16;
+
+  // state carried from psb_mesh to psb_power
+  bool mesh_ready = false;
+  psb_params par;
+  double bmin[3], bsize[3], bmax[3];
+  double shot[2], norm[2];
+
+  // timings
+  std::vector<Interval> intervals;
+  std::vector<cudaEvent_t> evpool;
+  double ms[PSB_T_COUNT];
+  double host_h2d_ms = 0;
+  long launches = 0;
+};
+
+struct psb_result {
+  int nbin = 0, nl = 0;
+  std::vector<double> k, kedge, km, lcnt, pl[2], xpl;
+  std::vector<unsigned long long> cnt;
+  bool has_pl[2] = {false, false}, has_xpl = false;
+  double shot[2] = {0, 0}, norm[2] = {0, 0};
+  double bmin[3], bsize[3], bmax[3];
+};
+
+namespace {
+
+cudaEvent_t get_event(psb_context *c) {
+  cudaEvent_t e;
+  if (!c->evpool.empty()) { e = c->evpool.back(); c->evpool.pop_back(); return e; }
+  cudaEventCreate(&e);
+  return e;
+}
+
+struct StageScope {
+  psb_context *c; int stage; cudaStream_t s; cudaEvent_t a;
+  StageScope(psb_context *c_, int stage_, cudaStream_t s_) : c(c_), stage(stage_), s(s_) {
+    a = get_event(c);
+    cudaEventRecord(a, s);
+  }
+  ~StageScope() {
+    cudaEvent_t b = get_event(c);
+    cudaEventRecord(b, s);
+    c->intervals.push_back({stage, a, b});
+  }
+};
+
+void reset_timings(psb_context *c) {
+  for (auto &iv : c->intervals) { c->evpool.push_back(iv.a); c->evpool.push_back(iv.b); }
+  c->intervals.clear();
+  for (double &m : c->ms) m = 0;
+  c->host_h2d_ms = 0;
+}
+
+void collect_timings(psb_context *c) {
+  for (auto &iv : c->intervals) {
+    float t = 0;
+    if (cudaEventElapsedTime(&t, iv.a, iv.b) == cudaSuccess) c->ms[iv.stage] += t;
+    c->evpool.push_back(iv.a);
+    c->evpool.push_back(iv.b);
+  }
+  c->intervals.clear();
+}
+
+int check_params(const psb_params *p) {
+  if (!p) { set_error("configuration parameters not loaded\n"); return -1; }
+  if (p->ncat < 1 || p->ncat > 2) { set_error("invalid number of catalogs: %d\n", p->ncat); return -1; }
+  if (p->assign < 0 || p->assign > 3) {
+    set_error("unrecognised particle assignment scheme: %d\n", p->assign); return -1;
+  }
+  if (p->gsize < 2 || p->gsize > 65536) {       // POWSPEC_MAX_GSIZE, src/define.h:66
+    set_error("invalid GRID_SIZE: %d\n", p->gsize); return -1;
+  }
+  if (p->npole < 1 || p->npole > 7) { set_error("invalid number of multipoles: %d\n", p->npole); return -1; }
+  for (int i = 0; i < p->npole; i++)
+    if (p->poles[i] < 0 || p->poles[i] > PSB_MAX_ELL || (i && p->poles[i] <= p->poles[i - 1])) {
+      set_error("multipoles must be sorted, unique and <= %d\n", PSB_MAX_ELL); return -1;
+    }
+  if (p->precision != 8 && p->precision != 4) { set_error("precision must be 8 or 4\n"); return -1; }
+  if (p->issim && !p->has_bsize) { set_error("BOX_SIZE is required for simulation boxes\n"); return -1; }
+  if (!(p->kbin > 0)) { set_error("invalid BIN_SIZE\n"); return -1; }
+  return 0;
+}
+
+// def_box, src/genr_mesh.c:509-578
+int define_box(const psb_params *p, const double lo[3], const double hi[3], double bmin[3],
+    double bsize[3]) {
+  const char ax[3] = {'x', 'y', 'z'};
+  for (int a = 0; a < 3; a++) {
+    if (lo[a] > hi[a]) { set_error("invalid %c coordinate value in the catalogs\n", ax[a]); return -1; }
+    if (p->issim) {
+      if (lo[a] < 0) { set_error("%c coordinate below 0: %lf\n", ax[a], lo[a]); return -1; }
+      if (hi[a] >= p->bsize[a]) {
+        set_error("%c coordinate not smaller than BOX_SIZE: %lf\n", ax[a], hi[a]); return -1;
+      }
+    }
+  }
+  for (int a = 0; a < 3; a++) {
+    if (p->issim) { bsize[a] = p->bsize[a]; bmin[a] = 0; }
+    else if (p->has_bsize) {
+      if (hi[a] - lo[a] > p->bsize[a]) {
+        set_error("BOX_SIZE is too small for the %c coordinates, should be at least %.10lg\n",
+            ax[a], hi[a] - lo[a]);
+        return -1;
+      }
+      bmin[a] = (hi[a] + lo[a] - p->bsize[a]) * 0.5;
+      bsize[a] = p->bsize[a];
+    }
+    else {
+      bsize[a] = ceil((hi[a] - lo[a]) * (1 + p->bpad[a]) / 10) * 10;    // POWSPEC_BOX_CEIL
+      bmin[a] = (hi[a] + lo[a] - bsize[a]) * 0.5;
+    }
+  }
+  if (p->verbose && !p->issim)
+    printf("  Box size: [%lg, %lg, %lg]\n"
+        "  Box boundaries: [[%lg,%lg], [%lg,%lg], [%lg,%lg]]\n", bsize[0], bsize[1], bsize[2],
+        bmin[0], bmin[0] + bsize[0], bmin[1], bmin[1] + bsize[1], bmin[2], bmin[2] + bsize[2]);
+  return 0;
+}
+
+// host -> device copy of a particle array.  Pinned sources go straight to the
+// copy engine; pageable ones are staged through two pinned buffers filled by a
+// few host threads, so the PCIe transfer is not bound by one memcpy thread.
+int upload(psb_context *c, const double *src, size_t n, DevBuf &dst) {
+  const size_t bytes = n * 32;
+  if (dst.reserve(bytes ? bytes : 32)) return -1;
+  if (!n) return 0;
+  cudaPointerAttributes at;
+  bool pinned = false;
+  if (cudaPointerGetAttributes(&at, src) == cudaSuccess)
+    pinned = (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged);
+  cudaGetLastError();
+  StageScope sc(c, PSB_T_H2D, c->st);
+  if (pinned) {
+    PSB_CUDA(cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyHostToDevice, c->st));
+    return 0;
+  }
+  const size_t CH = (size_t) 64 << 20;
+  if (!c->pinned[0]) {
+    for (int i = 0; i < 2; i++) {
+      PSB_CUDA(cudaHostAlloc(&c->pinned[i], CH, cudaHostAllocDefault));
+      PSB_CUDA(cudaEventCreateWithFlags(&c->pinned_free[i], cudaEventDisableTiming));
+    }
+    c->pinned_bytes = CH;
+  }
+  unsigned hw = std::thread::hardware_concurrency();
+  const int nthr = (int) std::max(1u, std::min(8u, hw ? hw : 1u));
+  size_t off = 0;
+  int slot = 0;
+  while (off < bytes) {
+    const size_t len = std::min(CH, bytes - off);
+    PSB_CUDA(cudaEventSynchronize(c->pinned_free[slot]));
+    char *stage = static_cast<char *>(c->pinned[slot]);
+    const char *from = reinterpret_cast<const char *>(src) + off;
+    if (nthr == 1 || len < ((size_t) 4 << 20)) memcpy(stage, from, len);
+    else {
+      std::vector<std::thread> th;
+      const size_t per = (len / nthr + 4095) & ~(size_t) 4095;
+      for (int t = 0; t < nthr; t++) {
+        const size_t a = std::min(len, per * t), b = std::min(len, per * (t + 1));
+        if (b > a) th.emplace_back([=] { memcpy(stage + a, from + a, b - a); });
+      }
+      for (auto &t : th) t.join();
+    }
+    PSB_CUDA(cudaMemcpyAsync(dst.as<char>() + off, stage, len, cudaMemcpyHostToDevice, c->st));
+    PSB_CUDA(cudaEventRecord(c->pinned_free[slot], c->st));
+    off += len;
+    slot ^= 1;
+  }
+  return 0;
+}
+
+int coordinate_bounds(psb_context *c, const double *dev, size_t n, double lo[3], double hi[3]) {
+  if (!n) return 0;
+  const int nblk = c->sms * 8;
+  if (c->bounds_part.reserve(sizeof(double) * 6 * nblk)) return -1;
+  {
+    StageScope sc(c, PSB_T_BOUNDS, c->st);
+    if (launch_bounds(dev, n, c->bounds_part.as<double>(), nblk, c->st)) return -1;
+    c->launches++;
+  }
+  std::vector<double> h(6 * (size_t) nblk);
+  PSB_CUDA(cudaMemcpyAsync(h.data(), c->bounds_part.p, h.size() * sizeof(double),
+      cudaMemcpyDeviceToHost, c->st));
+  PSB_CUDA(cudaStreamSynchronize(c->st));
+  for (int b = 0; b < nblk; b++)
+    for (int a = 0; a < 3; a++) {
+      lo[a] = std::min(lo[a], h[6 * b + a]);
+      hi[a] = std::max(hi[a], h[6 * b + 3 + a]);
+    }
+  return 0;
+}
+
+// counting sort by mesh row, then the scatter.  Chunked so that 32-bit offsets
+// suffice and the scratch stays bounded.
+int assign_catalog(psb_context *c, const double *dev, size_t n, const AssignGeom &g, int scheme,
+    int precision, double wscale, void *m0, void *m1) {
+  if (!n) return 0;
+  const bool do_sort = c->opt_sort && n >= (size_t) c->opt_sort_min;
+  if (!do_sort) {
+    StageScope sc(c, PSB_T_ASSIGN, c->st);
+    c->launches++;
+    return launch_assign(dev, n, g, scheme, precision, wscale, m0, m1, c->st);
+  }
+  const size_t CH = (size_t) 1 << 28;   // particles per chunk (8.6 GB of records)
+  const size_t nrow = (size_t) g.ng * g.ng;
+  const size_t chunk_max = std::min(n, CH);
+  if (c->keys.reserve(chunk_max * 4) || c->sorted.reserve(chunk_max * 32) ||
+      c->hist.reserve(nrow * 4) || c->cursor.reserve(nrow * 4))
+    return -1;
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->hist.as<uint32_t>(),
+      c->cursor.as<uint32_t>(), (int) nrow, c->st);
+  if (c->cubtmp.reserve(tmp_bytes)) return -1;
+  for (size_t off = 0; off < n; off += CH) {
+    const size_t len = std::min(CH, n - off);
+    const double *src = dev + 4 * off;
+    {
+      StageScope sc(c, PSB_T_SORT, c->st);
+      PSB_CUDA(cudaMemsetAsync(c->hist.p, 0, nrow * 4, c->st));
+      if (launch_row_keys(src, len, g, c->keys.as<uint32_t>(), c->hist.as<uint32_t>(), c->st))
+        return -1;
+      PSB_CUDA(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp_bytes, c->hist.as<uint32_t>(),
+          c->cursor.as<uint32_t>(), (int) nrow, c->st));
+      if (launch_row_scatter(src, len, c->keys.as<uint32_t>(), c->cursor.as<uint32_t>(),
+            c->sorted.as<double>(), c->st))
+        return -1;
+      c->launches += 5;
+    }
+    StageScope sc(c, PSB_T_ASSIGN, c->st);
+    if (launch_assign(c->sorted.as<double>(), len, g, scheme, precision, wscale, m0, m1, c->st))
+      return -1;
+    c->launches++;
+  }
+  return 0;
+}
+
+// alias_corr, src/multipole.c:46-100 — evaluated on the host with libm for the
+// 3 x Ng distinct arguments; the signed `x > 0.01` test reproduces quirk Q1.
+double window_axis(int intlace, int scheme, double x) {
+  if (intlace) {
+    double f;
+    if (x > 0.01) f = x / sin(x);
+    else {
+      const double t = x * x;
+      f = 1 + 0x1.5555555555555p-3 * t + 0x1.3e93e93e93e94p-6 * t * t
+        + 0x1.0cbb766210cbbp-9 * t * t * t;
+    }
+    f *= f;
+    switch (scheme) {
+      case 0: return f;
+      case 1: return f * f;
+      case 2: return f * f * f;
+      default: f *= f; return f * f;
+    }
+  }
+  double s;
+  if (x > 0.01) s = sin(x);
+  else {
+    const double t = x * x;
+    s = (1 - 0x1.5555555555555p-3 * t + 0x1.1111111111111p-7 * t * t
+        - 0x1.a01a01a01a01ap-13 * t * t * t) * x;
+  }
+  s *= s;
+  switch (scheme) {
+    case 0: return 1;
+    case 1: return 1 / (1 - 0x1.5555555555555p-1 * s);
+    case 2: return 1 / (1 - s + 0x1.1111111111111p-3 * s * s);
+    default: return 1 / (1 - 0x1.5555555555555p+0 * s + 0.4 * s * s
+                 - 0x1.a01a01a01a01ap-7 * s * s * s);
+  }
+}
+
+// the reference's bin decision for log bins, src/multipole.c:145-159, with libm
+int ref_log_bin(double k2, double k0, double k1, double dk, int nbin) {
+  const double kc = 0.5 * log10(k2);
+  if (kc < k0 || kc >= k1) return -1;
+  const int b = (int) ((kc - k0) / dk);
+  return (b < 0 || b >= nbin) ? -1 : b;
+}
+
+// smallest positive double x with pred(x) true, pred monotone false -> true
+template <typename F> double bisect_first(F pred) {
+  uint64_t lo = 1, hi = 0x7fefffffffffffffull;  // smallest subnormal .. DBL_MAX
+  auto val = [](uint64_t u) { double d; memcpy(&d, &u, 8); return d; };
+  if (!pred(val(hi))) return INFINITY;
+  while (lo < hi) {
+    const uint64_t mid = lo + (hi - lo) / 2;
+    if (pred(val(mid))) hi = mid; else lo = mid + 1;
+  }
+  return val(lo);
+}
+
+int ensure_plans(psb_context *c, int ng, int precision, bool need_inv) {
+  if (c->plan_ng != ng || c->plan_prec != precision) {
+    if (c->have_fwd) cufftDestroy(c->plan_fwd);
+    if (c->have_inv) cufftDestroy(c->plan_inv);
+    c->have_fwd = c->have_inv = false;
+    c->plan_ng = ng; c->plan_prec = precision;
+  }
+  const int ngk = ng / 2 + 1;
+  long long n[3] = {ng, ng, ng};
+  long long rembed[3] = {ng, ng, 2LL * ngk}, cembed[3] = {ng, ng, ngk};
+  const long long rdist = (long long) ng * ng * 2 * ngk, cdist = (long long) ng * ng * ngk;
+  size_t ws_f = 0, ws_i = 0;
+  if (!c->have_fwd) {
+    PSB_CUFFT(cufftCreate(&c->plan_fwd));
+    PSB_CUFFT(cufftSetAutoAllocation(c->plan_fwd, 0));
+    PSB_CUFFT(cufftMakePlanMany64(c->plan_fwd, 3, n, rembed, 1, rdist, cembed, 1, cdist,
+        precision == 8 ? CUFFT_D2Z : CUFFT_R2C, 1, &ws_f));
+    PSB_CUFFT(cufftSetStream(c->plan_fwd, c->st));
+    c->have_fwd = true;
+  }
+  else PSB_CUFFT(cufftGetSize(c->plan_fwd, &ws_f));
+  if (need_inv && !c->have_inv) {
+    PSB_CUFFT(cufftCreate(&c->plan_inv));
+    PSB_CUFFT(cufftSetAutoAllocation(c->plan_inv, 0));
+    PSB_CUFFT(cufftMakePlanMany64(c->plan_inv, 3, n, cembed, 1, cdist, rembed, 1, rdist,
+        precision == 8 ? CUFFT_Z2D : CUFFT_C2R, 1, &ws_i));
+    PSB_CUFFT(cufftSetStream(c->plan_inv, c->st));
+    c->have_inv = true;
+  }
+  else if (c->have_inv) PSB_CUFFT(cufftGetSize(c->plan_inv, &ws_i));
+  const size_t ws = std::max(ws_f, ws_i);
+  if (c->fftwork.reserve(ws ? ws : 256)) return -1;
+  PSB_CUFFT(cufftSetWorkArea(c->plan_fwd, c->fftwork.p));
+  if (c->have_inv) PSB_CUFFT(cufftSetWorkArea(c->plan_inv, c->fftwork.p));
+  return 0;
+}
+
+int fft_forward(psb_context *c, void *mesh) {
+  StageScope sc(c, PSB_T_FFT, c->st);
+  c->launches++;
+  if (c->plan_prec == 8)
+    PSB_CUFFT(cufftExecD2Z(c->plan_fwd, (cufftDoubleReal *) mesh, (cufftDoubleComplex *) mesh));
+  else
+    PSB_CUFFT(cufftExecR2C(c->plan_fwd, (cufftReal *) mesh, (cufftComplex *) mesh));
+  return 0;
+}
+
+int fft_inverse(psb_context *c, void *mesh) {
+  StageScope sc(c, PSB_T_FFT, c->st);
+  c->launches++;
+  if (c->plan_prec == 8)
+    PSB_CUFFT(cufftExecZ2D(c->plan_inv, (cufftDoubleComplex *) mesh, (cufftDoubleReal *) mesh));
+  else
+    PSB_CUFFT(cufftExecC2R(c->plan_inv, (cufftComplex *) mesh, (cufftReal *) mesh));
+  return 0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+const char *psb_last_error(void) { return get_error(); }
+
+int psb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+psb_context *psb_create(int device) {
+  int n = psb_device_count();
+  if (n <= 0) {
+    set_error("no CUDA device available: the powspec_b200 hot path has no CPU fallback\n");
+    return nullptr;
+  }
+  if (device < 0 || device >= n) { set_error("invalid CUDA device %d (have %d)\n", device, n); return nullptr; }
+  if (cudaSetDevice(device) != cudaSuccess) { set_error("cudaSetDevice(%d) failed\n", device); return nullptr; }
+  psb_context *c = new psb_context();
+  c->device = device;
+  cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, device);
+  if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->st_geom, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_geom, cudaEventDisableTiming) != cudaSuccess) {
+    set_error("failed to create CUDA streams\n");
+    delete c;
+    return nullptr;
+  }
+  for (double &m : c->ms) m = 0;
+  return c;
+}
+
+void psb_destroy(psb_context *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  if (c->have_fwd) cufftDestroy(c->plan_fwd);
+  if (c->have_inv) cufftDestroy(c->plan_inv);
+  for (int i = 0; i < 2; i++) {
+    for (int j = 0; j < 2; j++) { c->part_in[i][j].release(); c->mesh[i][j].release(); }
+    c->fkl[i].release(); c->fk0copy[i].release();
+    if (c->pinned[i]) cudaFreeHost(c->pinned[i]);
+    if (c->pinned_free[i]) cudaEventDestroy(c->pinned_free[i]);
+  }
+  c->fka.release(); c->sorted.release(); c->keys.release(); c->hist.release();
+  c->cursor.release(); c->cubtmp.release(); c->bounds_part.release(); c->fftwork.release();
+  c->tables.release(); c->binscratch.release(); c->bins.release();
+  reset_timings(c);
+  for (auto e : c->evpool) cudaEventDestroy(e);
+  if (c->ev_geom) cudaEventDestroy(c->ev_geom);
+  if (c->st) cudaStreamDestroy(c->st);
+  if (c->st_geom) cudaStreamDestroy(c->st_geom);
+  delete c;
+}
+
+int psb_set_option(psb_context *c, const char *name, long value) {
+  if (!c || !name) return -1;
+  if (!strcmp(name, "sort")) { c->opt_sort = value; return 0; }
+  if (!strcmp(name, "sort_min")) { c->opt_sort_min = value; return 0; }
+  set_error("unknown option: %s\n", name);
+  return -1;
+}
+
+// genr_mesh, src/genr_mesh.c:874-926
+int psb_mesh(psb_context *c, const psb_params *par, const psb_cats *cats) {
+  if (!c) { set_error("no device context\n"); return -1; }
+  if (check_params(par)) return -1;
+  if (!cats) { set_error("catalogs not read\n"); return -1; }
+  PSB_CUDA(cudaSetDevice(c->device));
+  reset_timings(c);
+  c->launches = 0;
+  c->mesh_ready = false;
+  c->par = *par;
+  const int nc = par->ncat, ng = par->gsize, prec = par->precision;
+  const int ngk = ng / 2 + 1, rowlen = 2 * ngk;
+  const size_t mesh_bytes = (size_t) ng * ng * rowlen * prec;
+
+  // particles to the device (if they are not there already) + bounds
+  const double *dptr[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  size_t cnt[2][2] = {{0, 0}, {0, 0}};
+  double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+  for (int i = 0; i < nc; i++)
+    for (int s = 0; s < (par->issim ? 1 : 2); s++) {
+      const double *src = s ? cats->rand[i] : cats->data[i];
+      const size_t n = s ? cats->nrand[i] : cats->ndata[i];
+      cnt[i][s] = n;
+      if (n && !src) { set_error("catalogs not read\n"); return -1; }
+      if (cats->memspace == PSB_MEM_DEVICE) dptr[i][s] = src;
+      else {
+        if (upload(c, src, n, c->part_in[i][s])) return -1;
+        dptr[i][s] = c->part_in[i][s].as<double>();
+      }
+      if (coordinate_bounds(c, dptr[i][s], n, lo, hi)) return -1;
+    }
+  for (int a = 0; a < 3; a++) c->bmax[a] = hi[a];
+  if (define_box(par, lo, hi, c->bmin, c->bsize)) return -1;
+
+  AssignGeom g;
+  memset(&g, 0, sizeof g);
+  g.ng = ng; g.rowlen = rowlen; g.nxloc = ng;
+  for (int a = 0; a < 3; a++) {
+    g.org[a] = c->bmin[a];
+    g.len[a] = c->bsize[a];
+    g.sorg[a] = c->bmin[a] - 0.5 * c->bsize[a] / ng;    // src/genr_mesh.c:817-818
+  }
+
+  // gen_dens, src/genr_mesh.c:793-858.  Randoms are scattered with weight
+  // -alpha * w into the data mesh (the reference builds a second mesh and
+  // subtracts, :802-806): one pass, no extra field.
+  for (int i = 0; i < nc; i++) {
+    const int nf = par->intlace ? 2 : 1;
+    for (int f = 0; f < nf; f++) {
+      if (c->mesh[i][f].reserve(mesh_bytes)) return -1;
+      StageScope sc(c, PSB_T_MEMSET, c->st);
+      PSB_CUDA(cudaMemsetAsync(c->mesh[i][f].p, 0, mesh_bytes, c->st));
+    }
+    void *m0 = c->mesh[i][0].p, *m1 = par->intlace ? c->mesh[i][1].p : nullptr;
+    if (assign_catalog(c, dptr[i][0], cnt[i][0], g, par->assign, prec, 1.0, m0, m1)) return -1;
+    if (!par->issim &&
+        assign_catalog(c, dptr[i][1], cnt[i][1], g, par->assign, prec, -cats->alpha[i], m0, m1))
+      return -1;
+    if (par->issim) {           // src/genr_mesh.c:904-909
+      const double vol = c->bsize[0] * c->bsize[1] * c->bsize[2];
+      c->shot[i] = vol / cats->wdata[i];
+      c->norm[i] = cats->wdata[i] * cats->wdata[i] / vol;
+    }
+    else { c->shot[i] = cats->shot[i]; c->norm[i] = cats->norm[i]; }
+    if (par->verbose) {
+      static const char *names[] = {"NGP", "CIC", "TSC", "PCS"};
+      if (nc == 2) printf("  Density field generated with %s for catalog %d\n", names[par->assign], i);
+      else printf("  Density field generated with %s for the catalog\n", names[par->assign]);
+    }
+  }
+  c->mesh_ready = true;
+  return 0;
+}
+
+int psb_mesh_box(const psb_context *c, double bmin[3], double bsize[3], double bmax[3]) {
+  if (!c || !c->mesh_ready) { set_error("meshes not generated\n"); return -1; }
+  for (int a = 0; a < 3; a++) { bmin[a] = c->bmin[a]; bsize[a] = c->bsize[a]; bmax[a] = c->bmax[a]; }
+  return 0;
+}
+
+int psb_copy_mesh(psb_context *c, int cat, int field, void *dst) {
+  if (!c || !c->mesh_ready || cat < 0 || cat >= c->par.ncat || field < 0 || field > 1 ||
+      (field == 1 && !c->par.intlace)) {
+    set_error("no such mesh\n");
+    return -1;
+  }
+  PSB_CUDA(cudaSetDevice(c->device));
+  const int ng = c->par.gsize, prec = c->par.precision;
+  const size_t bytes = (size_t) ng * ng * ng * prec;
+  DevBuf tmp;
+  if (tmp.reserve(bytes)) return -1;
+  int rc = launch_unpad_copy(c->mesh[cat][field].p, tmp.p, ng, 2 * (ng / 2 + 1), prec, c->st);
+  if (!rc && cudaMemcpyAsync(dst, tmp.p, bytes, cudaMemcpyDeviceToHost, c->st) != cudaSuccess) rc = -1;
+  if (cudaStreamSynchronize(c->st) != cudaSuccess) rc = -1;
+  tmp.release();
+  if (rc) set_error("failed to copy the mesh\n");
+  return rc;
+}
+
+// powspec, src/multipole.c:1179-1278
+psb_result *psb_power(psb_context *c, const psb_params *par) {
+  if (!c) { set_error("no device context\n"); return nullptr; }
+  if (check_params(par)) return nullptr;
+  if (!c->mesh_ready) { set_error("meshes not generated\n"); return nullptr; }
+  if (cudaSetDevice(c->device) != cudaSuccess) { set_error("cudaSetDevice failed\n"); return nullptr; }
+  const int nc = c->par.ncat, ng = c->par.gsize, prec = c->par.precision;
+  const int ngk = ng / 2 + 1;
+  const bool issim = c->par.issim, il = c->par.intlace;
+  const int nl = par->npole;
+  const int lmax = par->poles[nl - 1];
+  const bool need_ell = !issim && lmax > 0;
+  const size_t mesh_bytes = (size_t) ng * ng * 2 * ngk * prec;
+  const size_t ntot = (size_t) ng * ng * ng;
+
+  // ---- powspec_init, src/multipole.c:335-394
+  double bmax = std::max(c->bsize[0], std::max(c->bsize[1], c->bsize[2]));
+  double kny = PI * ng / bmax;
+  if (par->logscale) kny = log10(kny);
+  double kmax = kny;
+  if (par->kmax > 0 && kmax > par->kmax) kmax = par->kmax;
+  const double nbf = round((kmax - par->kmin) / par->kbin);
+  if (nbf >= INT_MAX) {
+    set_error("too many wave number bins due to the small bin size: %.10lg\n", par->kbin);
+    return nullptr;
+  }
+  int nbin = (int) nbf;
+  if (par->kmin + par->kbin * nbin > kny) nbin -= 1;
+  if (nbin < 1) {
+    set_error("not enough k bins given the Nyquist frequency and the bin size: %.10lg\n", par->kbin);
+    return nullptr;
+  }
+  psb_result *res = new psb_result();
+  res->nbin = nbin; res->nl = nl;
+  res->kedge.resize(nbin + 1); res->k.resize(nbin); res->km.assign(nbin, 0);
+  res->cnt.assign(nbin, 0); res->lcnt.assign((size_t) nl * nbin, 0);
+  for (int i = 0; i <= nbin; i++) res->kedge[i] = par->kmin + par->kbin * i;
+  for (int i = 0; i < nbin; i++) res->k[i] = (res->kedge[i] + res->kedge[i + 1]) * 0.5;
+  auto fail = [&]() { delete res; c->mesh_ready = false; return (psb_result *) nullptr; };
+
+  // ---- per-axis tables: k, k^2, window, interlace phase (3 x 5 x ng) + k^2 edges
+  const size_t tlen = (size_t) ng;
+  std::vector<double> &T = c->host_tables;
+  T.assign(15 * tlen + nbin + 1, 0.0);
+  const double fac = PI / ng;
+  for (int a = 0; a < 3; a++) {
+    const double vec = 2 * PI / c->bsize[a];    // src/multipole.c:113
+    double *kax = &T[(0 + a) * tlen], *kax2 = &T[(3 + a) * tlen], *wax = &T[(6 + a) * tlen];
+    double *pc = &T[(9 + a) * tlen], *ps = &T[(12 + a) * tlen];
+    for (int i = 0; i < ng; i++) {
+      const double n = (i <= (ng >> 1)) ? i : i - ng;
+      wax[i] = window_axis(il, c->par.assign, n * fac);
+      const double k = n * vec;
+      kax[i] = k;
+      kax2[i] = k * k;
+      const double ph = fac * n;                // src/multipole.c:468-476
+      pc[i] = cos(ph);
+      ps[i] = sin(ph);
+    }
+  }
+  if (par->logscale) {
+    const double k0 = res->kedge[0], k1 = res->kedge[nbin], dk = par->kbin;
+    double *e = &T[15 * tlen];
+    for (int b = 0; b < nbin; b++)
+      e[b] = bisect_first([&](double x) {
+        const double kc = 0.5 * log10(x);
+        if (kc >= k1) return true;
+        const int q = ref_log_bin(x, k0, k1, dk, nbin);
+        return q >= b;
+      });
+    e[nbin] = bisect_first([&](double x) { return 0.5 * log10(x) >= k1; });
+  }
+  if (c->tables.reserve(T.size() * sizeof(double))) return fail();
+  BinGeom bg;
+  memset(&bg, 0, sizeof bg);
+  bg.ng = ng; bg.ngk = ngk; bg.nbin = nbin; bg.nl = nl;
+  for (int i = 0; i < nl; i++) bg.poles[i] = par->poles[i];
+  bg.issim = issim; bg.logk = par->logscale; bg.intlace = il;
+  bg.y0 = 0; bg.nyloc = ng;
+  for (int a = 0; a < 3; a++) {
+    bg.los[a] = issim ? par->los[a] : 0.0;
+    const double *base = c->tables.as<double>();
+    bg.kax[a] = base + (0 + a) * tlen; bg.kax2[a] = base + (3 + a) * tlen;
+    bg.wax[a] = base + (6 + a) * tlen;
+    bg.pc[a] = base + (9 + a) * tlen; bg.ps[a] = base + (12 + a) * tlen;
+  }
+  bg.k2edge = par->logscale ? c->tables.as<double>() + 15 * tlen : nullptr;
+  bg.k0 = res->kedge[0]; bg.k1 = res->kedge[nbin]; bg.dk = par->kbin;
+
+  const size_t nacc = (size_t) nl * nbin;
+  const size_t sb = bin_scratch_bytes(bg);
+  // device bins: cnt (u64) | km | lcnt[nl*nbin] | pl0 | pl1 | xpl
+  const size_t bins_doubles = 2 * (size_t) nbin + 4 * nacc;
+  auto hard = [&](cudaError_t e) {
+    if (e != cudaSuccess) { set_error("CUDA failure: %s\n", cudaGetErrorString(e)); return true; }
+    return false;
+  };
+  if (c->binscratch.reserve(2 * sb) || c->bins.reserve(bins_doubles * sizeof(double))) return fail();
+  if (hard(cudaMemcpyAsync(c->tables.p, T.data(), T.size() * sizeof(double),
+          cudaMemcpyHostToDevice, c->st))) return fail();
+  if (hard(cudaMemsetAsync(c->bins.p, 0, bins_doubles * sizeof(double), c->st))) return fail();
+  unsigned long long *d_cnt = c->bins.as<unsigned long long>();
+  double *d_km = c->bins.as<double>() + nbin;
+  double *d_lcnt = d_km + nbin;
+  double *d_pl[2] = {d_lcnt + nacc, d_lcnt + 2 * nacc};
+  double *d_xpl = d_lcnt + 3 * nacc;
+  double *scratch_geom = c->binscratch.as<double>();
+  double *scratch_bin = reinterpret_cast<double *>(c->binscratch.as<char>() + sb);
+
+  // ---- powspec_precomp, src/multipole.c:111-257: pure geometry, own stream so it
+  // overlaps the FFTs
+  if (hard(cudaEventRecord(c->ev_geom, c->st)) ||
+      hard(cudaStreamWaitEvent(c->st_geom, c->ev_geom, 0))) return fail();
+  {
+    StageScope sc(c, PSB_T_GEOM, c->st_geom);
+    if (launch_geometry(bg, d_cnt, d_km, d_lcnt, scratch_geom, sb, c->st_geom)) return fail();
+    c->launches += 3;
+  }
+  if (hard(cudaEventRecord(c->ev_geom, c->st_geom))) return fail();
+
+  // ---- dens_k0, src/multipole.c:435-505
+  if (ensure_plans(c, ng, prec, need_ell && il)) return fail();
+  if (par->verbose) printf("  Alias corrections and wave numbers are pre-computed\n");
+  void *Fk0[2] = {nullptr, nullptr}, *Fk1[2] = {nullptr, nullptr}, *Fr[2] = {nullptr, nullptr};
+  for (int i = 0; i < nc; i++) {
+    void *A = c->mesh[i][0].p, *B = il ? c->mesh[i][1].p : nullptr;
+    if (need_ell && !il) {
+      // the real-space field is needed again for l > 0: transform a copy
+      if (c->fk0copy[i].reserve(mesh_bytes)) return fail();
+      if (hard(cudaMemcpyAsync(c->fk0copy[i].p, A, mesh_bytes, cudaMemcpyDeviceToDevice, c->st)))
+        return fail();
+      if (fft_forward(c, c->fk0copy[i].p)) return fail();
+      Fk0[i] = c->fk0copy[i].p; Fr[i] = A;
+    }
+    else {
+      if (fft_forward(c, A)) return fail();
+      Fk0[i] = A;
+    }
+    if (par->verbose) {
+      if (nc != 2) printf("  Done with computing 1 FFT for l = 0\n");
+      else printf("  Done with computing 1 FFT for l = 0 with catalog %d\n", i + 1);
+    }
+    if (il) {
+      if (fft_forward(c, B)) return fail();
+      if (issim) Fk1[i] = B;    // combined on the fly inside the binning kernel
+      else {
+        StageScope sc(c, PSB_T_BIN, c->st);
+        if (launch_combine(bg, prec, A, B, c->st)) return fail();
+        c->launches++;
+      }
+      if (need_ell) {
+        // back-transform of the combined field (src/multipole.c:489-500); for
+        // sims nothing reads it (quirk Q4) so it is skipped there
+        if (hard(cudaMemcpyAsync(B, A, mesh_bytes, cudaMemcpyDeviceToDevice, c->st))) return fail();
+        if (fft_inverse(c, B)) return fail();
+        if (launch_scale(B, mesh_bytes / prec, 1.0 / (double) ntot, prec, c->st)) return fail();
+        c->launches++;
+        Fr[i] = B;
+      }
+      if (par->verbose) printf("  Done with computing 2 FFTs for grid interlacing\n");
+    }
+  }
+
+  // ---- mode counting
+  if (issim) {
+    for (int i = 0; i < nc; i++) {
+      if (!par->isauto[i]) continue;
+      StageScope sc(c, PSB_T_BIN, c->st);
+      if (launch_bin(bg, prec, Fk0[i], Fk1[i], Fk0[i], Fk1[i], d_pl[i], scratch_bin, sb, c->st))
+        return fail();
+      c->launches += 2;
+      res->has_pl[i] = true;
+    }
+    if (par->iscross && nc == 2) {
+      StageScope sc(c, PSB_T_BIN, c->st);
+      if (launch_bin(bg, prec, Fk0[0], Fk1[0], Fk0[1], Fk1[1], d_xpl, scratch_bin, sb, c->st))
+        return fail();
+      c->launches += 2;
+      res->has_xpl = true;
+    }
+  }
+  else {
+    if (par->poles[0] == 0) {
+      for (int i = 0; i < nc; i++) {
+        if (!par->isauto[i]) continue;
+        StageScope sc(c, PSB_T_BIN, c->st);
+        if (launch_bin(bg, prec, Fk0[i], nullptr, Fk0[i], nullptr, d_pl[i], scratch_bin, sb, c->st))
+          return fail();
+        c->launches += 2;
+      }
+      if (par->iscross && nc == 2) {
+        StageScope sc(c, PSB_T_BIN, c->st);
+        if (launch_bin(bg, prec, Fk0[0], nullptr, Fk0[1], nullptr, d_xpl, scratch_bin, sb, c->st))
+          return fail();
+        c->launches += 2;
+      }
+    }
+    for (int i = 0; i < nc; i++) res->has_pl[i] = par->isauto[i];
+    res->has_xpl = par->iscross && nc == 2;
+    // the reference's loop starts at the second multipole whatever the first is
+    // (src/multipole.c:1229-1237)
+    for (int n = 1; n < nl; n++) {
+      const int ell = par->poles[n];
+      if (c->fka.reserve(mesh_bytes)) return fail();
+      for (int i = 0; i < nc; i++) {
+        if (c->fkl[i].reserve(mesh_bytes)) return fail();
+        if (hard(cudaMemsetAsync(c->fkl[i].p, 0, mesh_bytes, c->st))) return fail();
+        YlmGeom yg;
+        yg.ng = ng; yg.ngk = ngk; yg.rowlen = 2 * ngk; yg.ell = ell;
+        for (int a = 0; a < 3; a++) {
+          yg.smin[a] = c->bmin[a] * ng / c->bsize[a];   // src/genr_mesh.c:913-914
+          yg.bsize[a] = c->bsize[a];
+        }
+        for (int m = -ell; m <= ell; m++) {
+          yg.m = m;
+          {
+            StageScope sc(c, PSB_T_YLM, c->st);
+            if (launch_ylm_weight_r(yg, prec, Fr[i], c->fka.p, c->st)) return fail();
+            c->launches++;
+          }
+          if (fft_forward(c, c->fka.p)) return fail();
+          StageScope sc(c, PSB_T_YLM, c->st);
+          if (launch_ylm_accum_k(yg, bg, prec, c->fka.p, c->fkl[i].p, c->st)) return fail();
+          c->launches++;
+        }
+        if (par->verbose) {
+          if (nc != 2) printf("  Done with computing %d FFTs for l = %d\n", 2 * ell + 1, ell);
+          else printf("  Done with computing %d FFTs for l = %d with catalog %d\n", 2 * ell + 1, ell, i + 1);
+        }
+      }
+      StageScope sc(c, PSB_T_BIN, c->st);
+      for (int i = 0; i < nc; i++) {
+        if (!par->isauto[i]) continue;
+        if (launch_bin(bg, prec, Fk0[i], nullptr, c->fkl[i].p, nullptr, d_pl[i] + (size_t) n * nbin,
+              scratch_bin, sb, c->st))
+          return fail();
+        c->launches += 2;
+      }
+      if (par->iscross && nc == 2) {
+        if (launch_bin(bg, prec, Fk0[0], nullptr, c->fkl[1].p, nullptr, d_xpl + (size_t) n * nbin,
+              scratch_bin, sb, c->st) ||
+            launch_bin(bg, prec, Fk0[1], nullptr, c->fkl[0].p, nullptr, d_xpl + (size_t) n * nbin,
+              scratch_bin, sb, c->st))
+          return fail();
+        c->launches += 4;
+      }
+    }
+  }
+
+  // ---- results back: a few thousand doubles
+  if (hard(cudaStreamWaitEvent(c->st, c->ev_geom, 0))) return fail();
+  std::vector<double> hb(bins_doubles);
+  if (hard(cudaMemcpyAsync(hb.data(), c->bins.p, bins_doubles * sizeof(double),
+          cudaMemcpyDeviceToHost, c->st)) || hard(cudaStreamSynchronize(c->st)))
+    return fail();
+  collect_timings(c);
+  memcpy(res->cnt.data(), hb.data(), nbin * sizeof(double));
+  memcpy(res->km.data(), hb.data() + nbin, nbin * sizeof(double));
+  if (issim) memcpy(res->lcnt.data(), hb.data() + 2 * nbin, nacc * sizeof(double));
+  for (int b = 0; b < nbin; b++) if (res->cnt[b]) res->km[b] /= res->cnt[b];
+  for (int i = 0; i < 2; i++)
+    if (res->has_pl[i]) res->pl[i].assign(hb.begin() + 2 * nbin + (1 + i) * nacc,
+        hb.begin() + 2 * nbin + (2 + i) * nacc);
+  if (res->has_xpl) res->xpl.assign(hb.begin() + 2 * nbin + 3 * nacc, hb.begin() + 2 * nbin + 4 * nacc);
+
+  // ---- count_mode normalisation, src/multipole.c:1047-1161
+  const double *shot = c->shot, *norm = c->norm;
+  if (issim) {
+    for (int i = 0; i < nc; i++) {
+      if (!res->has_pl[i]) continue;
+      for (int l = 0; l < nl; l++)
+        for (int b = 0; b < nbin; b++) {
+          double &p = res->pl[i][(size_t) l * nbin + b];
+          if (res->cnt[b]) {
+            p /= norm[i] * res->cnt[b];
+            p -= shot[i] * res->lcnt[(size_t) l * nbin + b] / res->cnt[b];
+          }
+          p *= 2 * par->poles[l] + 1;
+        }
+    }
+    if (res->has_xpl)
+      for (int l = 0; l < nl; l++)
+        for (int b = 0; b < nbin; b++) {
+          double &p = res->xpl[(size_t) l * nbin + b];
+          if (res->cnt[b]) p /= sqrt(norm[0] * norm[1]) * res->cnt[b];
+          p *= 2 * par->poles[l] + 1;
+        }
+  }
+  else {
+    for (int i = 0; i < nc; i++) {
+      if (!res->has_pl[i]) continue;
+      if (par->poles[0] == 0)
+        for (int b = 0; b < nbin; b++)
+          if (res->cnt[b]) {
+            double &p = res->pl[i][b];
+            p = p / res->cnt[b] - shot[i];
+            p /= norm[i];
+          }
+      for (int n = 1; n < nl; n++)
+        for (int b = 0; b < nbin; b++)
+          if (res->cnt[b]) res->pl[i][(size_t) n * nbin + b] *= 4 * PI / (norm[i] * res->cnt[b]);
+    }
+    if (res->has_xpl) {
+      if (par->poles[0] == 0)
+        for (int b = 0; b < nbin; b++)
+          if (res->cnt[b]) res->xpl[b] /= sqrt(norm[0] * norm[1]) * res->cnt[b];
+      for (int n = 1; n < nl; n++)
+        for (int b = 0; b < nbin; b++)
+          if (res->cnt[b])
+            res->xpl[(size_t) n * nbin + b] *= 2 * PI / (sqrt(norm[0] * norm[1]) * res->cnt[b]);
+    }
+  }
+  if (par->logscale) {          // quirk Q7, src/multipole.c:1267-1274
+    for (int i = 0; i < nbin; i++) {
+      res->k[i] = pow(10, res->k[i]);
+      res->km[i] = pow(10, res->k[i]);
+      res->kedge[i] = pow(10, res->k[i]);
+    }
+    res->kedge[nbin] = pow(10, res->kedge[nbin]);
+  }
+  for (int i = 0; i < 2; i++) { res->shot[i] = i < nc ? shot[i] : 0; res->norm[i] = i < nc ? norm[i] : 0; }
+  for (int a = 0; a < 3; a++) { res->bmin[a] = c->bmin[a]; res->bsize[a] = c->bsize[a]; res->bmax[a] = c->bmax[a]; }
+  c->mesh_ready = false;        // the FFTs ran in place: the meshes are consumed
+  c->ms[PSB_T_TOTAL] = 0;
+  for (int s = 0; s < PSB_T_TOTAL; s++) c->ms[PSB_T_TOTAL] += c->ms[s];
+  return res;
+}
+
+psb_result *psb_run(psb_context *c, const psb_params *par, const psb_cats *cats) {
+  if (psb_mesh(c, par, cats)) return nullptr;
+  return psb_power(c, par);
+}
+
+void psb_result_free(psb_result *r) { delete r; }
+int psb_result_nbin(const psb_result *r) { return r ? r->nbin : -1; }
+int psb_result_nl(const psb_result *r) { return r ? r->nl : -1; }
+
+long psb_result_get(const psb_result *r, int what, int idx, void *dst) {
+  if (!r || !dst) return -1;
+  auto put = [&](const void *src, size_t n, size_t sz) { memcpy(dst, src, n * sz); return (long) n; };
+  switch (what) {
+    case PSB_GET_K: return put(r->k.data(), r->k.size(), 8);
+    case PSB_GET_KEDGE: return put(r->kedge.data(), r->kedge.size(), 8);
+    case PSB_GET_KM: return put(r->km.data(), r->km.size(), 8);
+    case PSB_GET_CNT: return put(r->cnt.data(), r->cnt.size(), 8);
+    case PSB_GET_LCNT: return put(r->lcnt.data(), r->lcnt.size(), 8);
+    case PSB_GET_PL:
+      if (idx < 0 || idx > 1 || !r->has_pl[idx]) return -1;
+      return put(r->pl[idx].data(), r->pl[idx].size(), 8);
+    case PSB_GET_XPL:
+      if (!r->has_xpl) return -1;
+      return put(r->xpl.data(), r->xpl.size(), 8);
+    case PSB_GET_SHOT: return put(r->shot, 2, 8);
+    case PSB_GET_NORM: return put(r->norm, 2, 8);
+    case PSB_GET_BMIN: return put(r->bmin, 3, 8);
+    case PSB_GET_BSIZE: return put(r->bsize, 3, 8);
+    case PSB_GET_BMAX: return put(r->bmax, 3, 8);
+    default: return -1;
+  }
+}
+
+int psb_timings(const psb_context *c, double *ms, int n) {
+  if (!c || !ms) return -1;
+  for (int i = 0; i < n && i < PSB_T_COUNT; i++) ms[i] = c->ms[i];
+  return std::min(n, (int) PSB_T_COUNT);
+}
+
+long psb_launch_count(const psb_context *c) { return c ? c->launches : -1; }
+
+double *psb_generate_catalog(psb_context *c, size_t n, double boxsize, int kind, uint64_t seed) {
+  if (!c) { set_error("no device context\n"); return nullptr; }
+  if (cudaSetDevice(c->device) != cudaSuccess) return nullptr;
+  void *p = nullptr;
+  if (cudaMalloc(&p, (n ? n : 1) * 32) != cudaSuccess) {
+    set_error("failed to allocate the synthetic catalogue\n");
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (launch_generate((double *) p, n, boxsize, kind, seed, c->st) ||
+      cudaStreamSynchronize(c->st) != cudaSuccess) {
+    cudaFree(p);
+    return nullptr;
+  }
+  return (double *) p;
+}
+
+void psb_device_free(psb_context *c, void *ptr) {
+  if (c) cudaSetDevice(c->device);
+  if (ptr) cudaFree(ptr);
+}
+
+int psb_copy_to_host(psb_context *c, void *dst, const void *src, size_t bytes) {
+  if (!c) return -1;
+  PSB_CUDA(cudaSetDevice(c->device));
+  PSB_CUDA(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+// Internal declarations shared by the translation units of libpowspec_b200.so.
+// Not installed; the public ABI is include/powspec_b200.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+
+namespace psb {
+
+// ---------------------------------------------------------------------------
+// error handling: message in the reference's P_ERR style (src/define.h:102,129)
+// ---------------------------------------------------------------------------
+void set_error(const char *fmt, ...);
+const char *get_error();
+
+#define PSB_CUDA(call)                                                          \
+  do {                                                                          \
+    cudaError_t e_ = (call);                                                    \
+    if (e_ != cudaSuccess) {                                                    \
+      psb::set_error("CUDA failure %s at %s:%d: %s\n", #call, __FILE__,         \
+          __LINE__, cudaGetErrorString(e_));                                    \
+      return -1;                                                                \
+    }                                                                           \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// geometry of one assignment pass
+// ---------------------------------------------------------------------------
+struct AssignGeom {
+  int ng;               // cells per side
+  int rowlen;           // reals per z-row of the (padded, in-place FFT) mesh
+  int x0;               // first x-plane held locally (slab decomposition)
+  int nxloc;            // number of local x-planes incl. halo planes
+  int xhalo_lo;         // halo planes below x0 (wrapped)
+  double org[3];        // lower box corner (MESH.min)
+  double sorg[3];       // corner of the half-cell shifted box (MESH.smin)
+  double len[3];        // box size
+};
+
+// launch wrappers (assign.cu).  All asynchronous on `st`; return 0 / -1.
+int launch_bounds(const double *p, size_t n, double *partials /*[nblk*6]*/,
+    int nblk, cudaStream_t st);
+int launch_row_keys(const double *p, size_t n, const AssignGeom &g,
+    uint32_t *keys, uint32_t *hist, cudaStream_t st);
+int launch_row_scatter(const double *p, size_t n, const uint32_t *keys,
+    uint32_t *cursor, double *sorted, cudaStream_t st);
+// mesh1 may be null (no interlacing).  precision: 8 or 4.
+int launch_assign(const double *p, size_t n, const AssignGeom &g, int scheme,
+    int precision, double wscale, void *mesh0, void *mesh1, cudaStream_t st);
+int launch_unpad_copy(const void *mesh, void *dst, int ng, int rowlen,
+    int precision, cudaStream_t st);
+
+// ---------------------------------------------------------------------------
+// Fourier-space binning (binning.cu)
+// ---------------------------------------------------------------------------
+struct BinGeom {
+  int ng, ngk;
+  int nbin, nl;
+  int poles[8];
+  int issim, logk, intlace;
+  int y0, nyloc;        // local range of the slowest index of the k-space array
+  double los[3];
+  double k0;            // kedge[0]
+  double k1;            // kedge[nbin]
+  double dk;
+  // device tables, each of length ng (axis 2: ngk entries used)
+  const double *kax[3];         // k_a(n)        src/multipole.c:130-141
+  const double *kax2[3];        // k_a(n)^2
+  const double *wax[3];         // window factor src/multipole.c:46-100
+  const double *pc[3], *ps[3];  // cos/sin(pi n / Ng), interlace phase, :462-484
+  const double *k2edge;         // [nbin+1] thresholds in k^2 (log bins) or null
+};
+
+// geometry-only pass: cnt (u64), km (sum of |k| or log k), lcnt[nl][nbin]
+int launch_geometry(const BinGeom &g, unsigned long long *cnt, double *km,
+    double *lcnt, double *scratch, size_t scratch_bytes, cudaStream_t st);
+// data pass: pl[nl][nbin] += sum Re(Fa conj Fb) alias mult L_l(mu)   (sims)
+//            pl[nbin]     += sum Re(Fa conj Fb) alias mult           (surveys)
+// Fa0/Fb0: fields on the base grid; Fa1/Fb1: shifted-grid fields combined on
+// the fly (null if not interlaced or already combined).
+int launch_bin(const BinGeom &g, int precision, const void *Fa0, const void *Fa1,
+    const void *Fb0, const void *Fb1, double *pl, double *scratch,
+    size_t scratch_bytes, cudaStream_t st);
+size_t bin_scratch_bytes(const BinGeom &g);
+// in-place interlace combination F0 <- (F0 + phase F1)/2 (survey l>0 needs the field)
+int launch_combine(const BinGeom &g, int precision, void *F0, const void *F1,
+    cudaStream_t st);
+// survey multipoles (src/mp_template.c): out = Fr * Y_lm(r) ; Fkl += Fka * Y_lm(k)
+struct YlmGeom {
+  int ng, ngk, rowlen, ell, m;
+  double smin[3];       // grid coordinate of the box corner (src/genr_mesh.c:913-914)
+  double bsize[3];
+};
+int launch_ylm_weight_r(const YlmGeom &g, int precision, const void *Fr, void *out,
+    cudaStream_t st);
+int launch_ylm_accum_k(const YlmGeom &g, const BinGeom &bg, int precision,
+    const void *Fka, void *Fkl, cudaStream_t st);
+int launch_scale(void *mesh, size_t n, double factor, int precision, cudaStream_t st);
+
+// generate.cu
+int launch_generate(double *out, size_t n, double boxsize, int kind, uint64_t seed,
+    cudaStream_t st);
+
+}  // namespace psb

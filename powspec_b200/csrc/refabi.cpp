@@ -1,0 +1,216 @@
+// The reference's seam: genr_mesh / mesh_destroy / powspec / powspec_destroy /
+// powspec_assign_names with the reference's signatures and struct layouts
+// (include/powspec_refabi.h), implemented on the psb_* device path.  This is
+// what the reference's unchanged C host (powspec.c, load_conf.c, read_cata.c,
+// cnvt_coord.c, save_res.c) links against instead of genr_mesh.o + multipole.o.
+//
+// Behaviour kept from the reference: progress text on stdout
+// ("Generating meshes for FFT ..." / FMT_DONE, src/genr_mesh.c:875,924;
+// "Evaluating power spectra ...", src/multipole.c:1180,1276), NULL + P_ERR-style
+// message on failure, genr_mesh takes ownership of (frees) the particle arrays
+// (src/genr_mesh.c:917-922) and writes cat->shot/norm for simulation boxes
+// (:904-909), powspec leaves MESH metadata alive for save_res, PK arrays are
+// plain malloc memory laid out as powspec_init does (src/multipole.c:306-421).
+//
+// Runtime knobs the reference fixes at compile time:
+//   POWSPEC_B200_PRECISION = 8 | 4   (the reference's -DSINGLE_PREC, Makefile:14)
+//   POWSPEC_B200_DEVICE    = CUDA device ordinal (default 0)
+
+#include "../../include/powspec_b200.h"
+#include "../../include/powspec_refabi.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#define FMT_DONE "\r\x1B[70C[\x1B[32;1mDONE\x1B[0m]\n"  /* src/define.h:104 */
+#define P_ERR(...) fprintf(stderr, "\n\x1B[31;1mError:\x1B[0m " __VA_ARGS__)
+
+static psb_context *g_ctx = nullptr;
+
+static int env_int(const char *name, int dflt) {
+  const char *s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+
+static void fill_params(const psb_ref_CONF *conf, psb_params *p) {
+  memset(p, 0, sizeof *p);
+  p->ncat = conf->ndata;
+  p->issim = conf->issim;
+  p->intlace = conf->intlace;
+  p->assign = conf->assign;
+  p->gsize = conf->gsize;
+  p->logscale = conf->logscale;
+  p->verbose = conf->verbose;
+  p->npole = conf->npole;
+  for (int i = 0; i < conf->npole && i < PSB_MAX_POLES; i++) p->poles[i] = conf->poles[i];
+  p->has_bsize = conf->bsize != nullptr;
+  p->isauto[0] = conf->isauto[0];
+  p->isauto[1] = conf->isauto[1];
+  p->iscross = conf->iscross;
+  for (int a = 0; a < 3; a++) {
+    p->los[a] = conf->los ? conf->los[a] : (a == 2 ? 1.0 : 0.0);
+    p->bsize[a] = conf->bsize ? conf->bsize[a] : 0.0;
+    p->bpad[a] = conf->bpad ? conf->bpad[a] : 0.02;     /* DEFAULT_BOX_PAD */
+  }
+  p->kmin = conf->kmin;
+  p->kmax = conf->kmax;
+  p->kbin = conf->kbin;
+  p->precision = env_int("POWSPEC_B200_PRECISION", 8);
+  p->device = env_int("POWSPEC_B200_DEVICE", 0);
+}
+
+extern "C" {
+
+const char *powspec_assign_names[] = {"NGP", "CIC", "TSC", "PCS"};
+
+psb_ref_MESH *genr_mesh(const psb_ref_CONF *conf, psb_ref_CATA *cat) {
+  printf("Generating meshes for FFT ...");
+  if (!conf) { P_ERR("configuration parameters not loaded\n"); return nullptr; }
+  if (conf->verbose) printf("\n");
+  fflush(stdout);
+  if (!cat) { P_ERR("catalogs not read\n"); return nullptr; }
+
+  psb_params par;
+  fill_params(conf, &par);
+  if (!g_ctx) g_ctx = psb_create(par.device);
+  if (!g_ctx) return nullptr;
+
+  psb_cats in;
+  memset(&in, 0, sizeof in);
+  in.memspace = PSB_MEM_HOST;
+  for (int i = 0; i < cat->num && i < 2; i++) {
+    in.data[i] = cat->data ? reinterpret_cast<const double *>(cat->data[i]) : nullptr;
+    in.rand[i] = cat->rand ? reinterpret_cast<const double *>(cat->rand[i]) : nullptr;
+    in.ndata[i] = cat->ndata[i];
+    in.nrand[i] = cat->nrand[i];
+    in.wdata[i] = cat->wdata[i];
+    in.wrand[i] = cat->wrand[i];
+    in.alpha[i] = cat->alpha[i];
+    in.shot[i] = cat->shot[i];
+    in.norm[i] = cat->norm[i];
+  }
+  if (psb_mesh(g_ctx, &par, &in)) return nullptr;
+
+  psb_ref_MESH *mesh = static_cast<psb_ref_MESH *>(calloc(1, sizeof *mesh));
+  if (!mesh) { P_ERR("failed to initalise the meshes\n"); return nullptr; }
+  mesh->num = conf->ndata;
+  mesh->Ng = conf->gsize;
+  mesh->Ngk = (mesh->Ng >> 1) + 1;
+  mesh->Ntot = (size_t) mesh->Ng * mesh->Ng * mesh->Ng;
+  mesh->Ncmplx = (size_t) mesh->Ng * mesh->Ng * mesh->Ngk;
+  mesh->issim = conf->issim;
+  mesh->intlace = conf->intlace;
+  mesh->assign = conf->assign;
+  mesh->fft_init = false;
+  /* box metadata as def_box leaves it, read by save_res (src/save_res.c:70-82) */
+  psb_mesh_box(g_ctx, mesh->min, mesh->bsize, mesh->max);
+  if (conf->issim) {            /* src/genr_mesh.c:904-909 */
+    for (int i = 0; i < cat->num; i++) {
+      const double vol = mesh->bsize[0] * mesh->bsize[1] * mesh->bsize[2];
+      cat->shot[i] = vol / cat->wdata[i];
+      cat->norm[i] = cat->wdata[i] * cat->wdata[i] / vol;
+    }
+  }
+  for (int a = 0; a < 3; a++) mesh->smin[a] = mesh->min[a] * mesh->Ng / mesh->bsize[a];
+
+  /* ownership of the particles ends here, as in the reference */
+  for (int i = 0; i < cat->num; i++) {
+    if (cat->data && cat->data[i]) free(cat->data[i]);
+    if (cat->rand && cat->rand[i]) free(cat->rand[i]);
+  }
+  free(cat->data); cat->data = nullptr;
+  free(cat->rand); cat->rand = nullptr;
+
+  printf(FMT_DONE);
+  return mesh;
+}
+
+void mesh_destroy(psb_ref_MESH *mesh) {
+  /* device buffers and cuFFT plans live in the context */
+  if (g_ctx) { psb_destroy(g_ctx); g_ctx = nullptr; }
+  free(mesh);
+}
+
+psb_ref_PK *powspec(const psb_ref_CONF *conf, const psb_ref_CATA *cat, psb_ref_MESH *mesh) {
+  printf("Evaluating power spectra ...");
+  if (!conf) { P_ERR("configuration parameters not loaded\n"); return nullptr; }
+  if (conf->verbose) printf("\n");
+  fflush(stdout);
+  if (!cat) { P_ERR("catalogs not read\n"); return nullptr; }
+  if (!mesh || !g_ctx) { P_ERR("meshes not generated\n"); return nullptr; }
+
+  psb_params par;
+  fill_params(conf, &par);
+  psb_result *res = psb_power(g_ctx, &par);
+  if (!res) return nullptr;
+
+  psb_ref_PK *pk = static_cast<psb_ref_PK *>(calloc(1, sizeof *pk));
+  const int nl = psb_result_nl(res), nb = psb_result_nbin(res);
+  bool ok = pk != nullptr;
+  if (ok) {
+    pk->issim = conf->issim; pk->log = conf->logscale;
+    if (pk->issim) for (int a = 0; a < 3; a++) pk->los[a] = conf->los[a];
+    pk->isauto[0] = conf->isauto[0]; pk->isauto[1] = conf->isauto[1];
+    pk->iscross = conf->iscross;
+    pk->nl = nl; pk->nbin = nb; pk->dk = conf->kbin; pk->nomp = 1;
+    pk->poles = static_cast<int *>(malloc(nl * sizeof(int)));
+    pk->kedge = static_cast<double *>(malloc((nb + 1) * sizeof(double)));
+    pk->k = static_cast<double *>(malloc(nb * sizeof(double)));
+    pk->km = static_cast<double *>(malloc(nb * sizeof(double)));
+    pk->cnt = static_cast<size_t *>(malloc(nb * sizeof(size_t)));
+    ok = pk->poles && pk->kedge && pk->k && pk->km && pk->cnt;
+    if (ok && pk->issim) ok = (pk->lcnt = static_cast<double *>(malloc(sizeof(double) * nl * nb))) != nullptr;
+  }
+  double *flat = ok ? static_cast<double *>(malloc(sizeof(double) * nl * nb)) : nullptr;
+  ok = ok && flat;
+  if (ok) {
+    memcpy(pk->poles, conf->poles, nl * sizeof(int));
+    psb_result_get(res, PSB_GET_KEDGE, 0, pk->kedge);
+    psb_result_get(res, PSB_GET_K, 0, pk->k);
+    psb_result_get(res, PSB_GET_KM, 0, pk->km);
+    psb_result_get(res, PSB_GET_CNT, 0, pk->cnt);      /* size_t == uint64 on LP64 */
+    if (pk->issim) psb_result_get(res, PSB_GET_LCNT, 0, pk->lcnt);
+    for (int c = 0; c <= 2 && ok; c++) {
+      const bool cross = c == 2;
+      if (cross ? !conf->iscross : !conf->isauto[c]) continue;
+      double **rows = static_cast<double **>(calloc(nl, sizeof(double *)));
+      if (!rows) { ok = false; break; }
+      if (cross) pk->xpl = rows; else pk->pl[c] = rows;
+      const long got = cross ? psb_result_get(res, PSB_GET_XPL, 0, flat)
+                             : psb_result_get(res, PSB_GET_PL, c, flat);
+      for (int l = 0; l < nl; l++) {
+        rows[l] = static_cast<double *>(calloc(nb, sizeof(double)));
+        if (!rows[l]) { ok = false; break; }
+        if (got > 0) memcpy(rows[l], flat + (size_t) l * nb, nb * sizeof(double));
+      }
+    }
+  }
+  free(flat);
+  psb_result_free(res);
+  if (!ok) {
+    P_ERR("failed to initialise the power spectra\n");
+    powspec_destroy(pk);
+    return nullptr;
+  }
+  printf(FMT_DONE);
+  return pk;
+}
+
+void powspec_destroy(psb_ref_PK *pk) {
+  if (!pk) return;
+  free(pk->poles); free(pk->kedge); free(pk->k); free(pk->km); free(pk->cnt); free(pk->lcnt);
+  for (int i = 0; i < 2; i++)
+    if (pk->pl[i]) {
+      for (int j = 0; j < pk->nl; j++) free(pk->pl[i][j]);
+      free(pk->pl[i]);
+    }
+  if (pk->xpl) {
+    for (int j = 0; j < pk->nl; j++) free(pk->xpl[j]);
+    free(pk->xpl);
+  }
+  free(pk->pcnt); free(pk->plcnt);
+  free(pk);
+}
+
+}  // extern "C"
