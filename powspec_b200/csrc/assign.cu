@@ -93,7 +93,10 @@ __global__ void __launch_bounds__(256) k_row_keys(const double2 *__restrict__ p,
     double2 a = __ldg(p + 2 * i);
     int cx = base_cell(grid_coord(a.x, g.org[0], g.len[0], g.ng), g.ng);
     int cy = base_cell(grid_coord(a.y, g.org[1], g.len[1], g.ng), g.ng);
-    uint32_t key = (uint32_t) cx * (uint32_t) g.ng + (uint32_t) cy;
+    // strip-major row order: the sweep over x stays inside a strip of
+    // g.strip rows, so the planes it touches fit in L2
+    uint32_t key = ((uint32_t) (cy / g.strip) * (uint32_t) g.ng + (uint32_t) cx)
+        * (uint32_t) g.strip + (uint32_t) (cy % g.strip);
     keys[i] = key;
     atomicAdd(hist + key, 1u);
   }
@@ -116,6 +119,11 @@ static int grid_for(size_t n, int per_block, int max_blocks) {
   if (b < 1) b = 1;
   if (b > (size_t) max_blocks) b = max_blocks;
   return (int) b;
+}
+
+size_t row_key_count(const AssignGeom &g) {
+  const size_t nstrip = ((size_t) g.ng + g.strip - 1) / g.strip;
+  return nstrip * (size_t) g.ng * (size_t) g.strip;
 }
 
 int launch_row_keys(const double *p, size_t n, const AssignGeom &g, uint32_t *keys,
@@ -217,8 +225,11 @@ __device__ __forceinline__ void scatter_one(const double x[3], double pw,
 template <int SCHEME, typename real, bool INTERLACE>
 __global__ void __launch_bounds__(256) k_assign(const double2 *__restrict__ p, size_t n,
     AssignGeom g, double wscale, real *__restrict__ mesh0, real *__restrict__ mesh1) {
-  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n;
-       i += (size_t) gridDim.x * blockDim.x) {
+  // one particle per thread, blocks in particle order: with the strip-sorted
+  // catalogue the set of mesh rows being updated moves monotonically, so every
+  // mesh sector is fetched into L2 once and written back once
+  const size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+  if (i < n) {
     double2 a = __ldg(p + 2 * i), b = __ldg(p + 2 * i + 1);
     double x[3] = {a.x, a.y, b.x};
     const double pw = b.y * wscale;
@@ -236,7 +247,9 @@ __global__ void __launch_bounds__(256) k_assign(const double2 *__restrict__ p, s
 template <int SCHEME, typename real>
 static int launch_assign_t(const double *p, size_t n, const AssignGeom &g, double wscale,
     void *m0, void *m1, cudaStream_t st) {
-  const int grid = grid_for(n, 256, 148 * 32);
+  const size_t nblk = (n + 255) / 256;
+  if (nblk > 0x7fffffffull) { set_error("too many particles in one assignment chunk\n"); return -1; }
+  const int grid = (int) nblk;
   const double2 *pp = reinterpret_cast<const double2 *>(p);
   if (m1)
     k_assign<SCHEME, real, true><<<grid, 256, 0, st>>>(pp, n, g, wscale,

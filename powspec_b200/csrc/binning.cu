@@ -115,10 +115,23 @@ __global__ void __launch_bounds__(256) k_spectrum(BinGeom g, const void *__restr
   __syncwarp();
 
   const bool cross = (Fb0 != Fa0);
-  const size_t nrows = (size_t) g.nyloc * g.ng;
+  // The mode-counting pass is pure geometry: when the line of sight has no x
+  // (y) component the summands are even in n_x (n_y) — k^2 tables are exactly
+  // symmetric — so only n >= 0 is visited and doubled (exact in binary FP).
+  const int half = (g.ng >> 1) + 1;
+  const int nI = (MODE == MODE_GEOM && g.symx) ? half : g.nyloc;
+  const int nJ = (MODE == MODE_GEOM && g.symy) ? half : g.ng;
+  const size_t nrows = (size_t) nI * nJ;
   const size_t wstride = (size_t) gridDim.x * nwarp;
   for (size_t row = (size_t) blockIdx.x * nwarp + warp; row < nrows; row += wstride) {
-    const int i = g.y0 + (int) (row / g.ng), j = (int) (row % g.ng);
+    const int i = g.y0 + (int) (row / nJ), j = (int) (row % nJ);
+    double wsym = 1.0;
+    if (MODE == MODE_GEOM) {
+      const bool self_i = (i == 0) || (((g.ng & 1) == 0) && i == (g.ng >> 1));
+      const bool self_j = (j == 0) || (((g.ng & 1) == 0) && j == (g.ng >> 1));
+      if (g.symx && !self_i) wsym *= 2.0;
+      if (g.symy && !self_j) wsym *= 2.0;
+    }
     const double ki = __ldg(g.kax[0] + i), kj = __ldg(g.kax[1] + j);
     const double k2ij = __dadd_rn(__ldg(g.kax2[0] + i), __ldg(g.kax2[1] + j));
     const double wij = __dmul_rn(__ldg(g.wax[0] + i), __ldg(g.wax[1] + j));
@@ -130,7 +143,7 @@ __global__ void __launch_bounds__(256) k_spectrum(BinGeom g, const void *__restr
       pcij = ci * cj - si * sj;
       psij = si * cj + ci * sj;
     }
-    const size_t rbase = row * (size_t) g.ngk;
+    const size_t rbase = ((size_t) (i - g.y0) * g.ng + j) * (size_t) g.ngk;
     for (int kb = 0; kb < g.ngk; kb += 32) {
       const int k = kb + lane;
       int key = -1;
@@ -155,7 +168,7 @@ __global__ void __launch_bounds__(256) k_spectrum(BinGeom g, const void *__restr
         if (MODE == MODE_SIM && k2 == 0.0) key = -1;
         if (key >= 0) {
           const bool edge = (k == 0) || (((g.ng & 1) == 0) && k == (g.ng >> 1));
-          const double mult = edge ? 1.0 : 2.0;
+          const double mult = (edge ? 1.0 : 2.0) * wsym;
           double p = 0.0;
           if (MODE != MODE_GEOM) {
             if (INTERLACE) {
@@ -267,7 +280,9 @@ int run_spectrum(const BinGeom &g, const void *Fa0, const void *Fa1, const void 
   const int nacc = NV * g.nbin;
   LaunchShape ls;
   if (shape_for(kern, nacc, ls)) return -1;
-  size_t rows = (size_t) g.nyloc * g.ng;
+  const int half = (g.ng >> 1) + 1;
+  size_t rows = (size_t) ((MODE == MODE_GEOM && g.symx) ? half : g.nyloc)
+      * ((MODE == MODE_GEOM && g.symy) ? half : g.ng);
   size_t need_blocks = (rows + ls.threads / 32 - 1) / (ls.threads / 32);
   if ((size_t) ls.blocks > need_blocks) ls.blocks = (int) need_blocks;
   if (ls.blocks > MAX_BLOCKS) ls.blocks = MAX_BLOCKS;

@@ -103,6 +103,10 @@ struct psb_context {
 
   // particles
   DevBuf part_in[2][2];                 // [cat][data|rand] staged copies of host arrays
+  DevBuf chunkbuf[2];                   // double-buffered device chunks of a streamed catalogue
+  cudaStream_t st_copy = nullptr;       // H2D engine stream of the streaming path
+  cudaEvent_t ev_filled[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
+  std::vector<double> bounds_host;      // per-chunk bounds partials of the streaming path
   DevBuf sorted, keys, hist, cursor, cubtmp, bounds_part;
   void *pinned[2] = {nullptr, nullptr};
   size_t pinned_bytes = 0;
@@ -125,6 +129,10 @@ struct psb_context {
   // options
   long opt_sort = 1;
   long opt_sort_min = 1 << 16;
+  long opt_geom_sym = 1;                // fold +-n_x, +-n_y in the mode-counting pass
+  long opt_strip = 64;                  // rows per strip of the sort order
+  long opt_stream = 1;                  // overlap H2D with assignment for host catalogues (sims)
+  long opt_stream_chunk = 1 << 24;      // particles per streamed chunk (512 MiB)
 
   // state carried from psb_mesh to psb_power
   bool mesh_ready = false;
@@ -244,56 +252,18 @@ int define_box(const psb_params *p, const double lo[3], const double hi[3], doub
   return 0;
 }
 
-// host -> device copy of a particle array.  Pinned sources go straight to the
-// copy engine; pageable ones are staged through two pinned buffers filled by a
-// few host threads, so the PCIe transfer is not bound by one memcpy thread.
+int h2d_async(psb_context *c, void *dst, const void *src, size_t bytes, bool pinned,
+    cudaStream_t stream);
+bool is_pinned(const void *p);
+
+// host -> device copy of a whole particle array (surveys: the box depends on
+// the bounds of all catalogues, so they are made resident first)
 int upload(psb_context *c, const double *src, size_t n, DevBuf &dst) {
   const size_t bytes = n * 32;
   if (dst.reserve(bytes ? bytes : 32)) return -1;
   if (!n) return 0;
-  cudaPointerAttributes at;
-  bool pinned = false;
-  if (cudaPointerGetAttributes(&at, src) == cudaSuccess)
-    pinned = (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged);
-  cudaGetLastError();
   StageScope sc(c, PSB_T_H2D, c->st);
-  if (pinned) {
-    PSB_CUDA(cudaMemcpyAsync(dst.p, src, bytes, cudaMemcpyHostToDevice, c->st));
-    return 0;
-  }
-  const size_t CH = (size_t) 64 << 20;
-  if (!c->pinned[0]) {
-    for (int i = 0; i < 2; i++) {
-      PSB_CUDA(cudaHostAlloc(&c->pinned[i], CH, cudaHostAllocDefault));
-      PSB_CUDA(cudaEventCreateWithFlags(&c->pinned_free[i], cudaEventDisableTiming));
-    }
-    c->pinned_bytes = CH;
-  }
-  unsigned hw = std::thread::hardware_concurrency();
-  const int nthr = (int) std::max(1u, std::min(8u, hw ? hw : 1u));
-  size_t off = 0;
-  int slot = 0;
-  while (off < bytes) {
-    const size_t len = std::min(CH, bytes - off);
-    PSB_CUDA(cudaEventSynchronize(c->pinned_free[slot]));
-    char *stage = static_cast<char *>(c->pinned[slot]);
-    const char *from = reinterpret_cast<const char *>(src) + off;
-    if (nthr == 1 || len < ((size_t) 4 << 20)) memcpy(stage, from, len);
-    else {
-      std::vector<std::thread> th;
-      const size_t per = (len / nthr + 4095) & ~(size_t) 4095;
-      for (int t = 0; t < nthr; t++) {
-        const size_t a = std::min(len, per * t), b = std::min(len, per * (t + 1));
-        if (b > a) th.emplace_back([=] { memcpy(stage + a, from + a, b - a); });
-      }
-      for (auto &t : th) t.join();
-    }
-    PSB_CUDA(cudaMemcpyAsync(dst.as<char>() + off, stage, len, cudaMemcpyHostToDevice, c->st));
-    PSB_CUDA(cudaEventRecord(c->pinned_free[slot], c->st));
-    off += len;
-    slot ^= 1;
-  }
-  return 0;
+  return h2d_async(c, dst.p, src, bytes, is_pinned(src), c->st);
 }
 
 int coordinate_bounds(psb_context *c, const double *dev, size_t n, double lo[3], double hi[3]) {
@@ -319,45 +289,168 @@ int coordinate_bounds(psb_context *c, const double *dev, size_t n, double lo[3],
 
 // counting sort by mesh row, then the scatter.  Chunked so that 32-bit offsets
 // suffice and the scratch stays bounded.
-int assign_catalog(psb_context *c, const double *dev, size_t n, const AssignGeom &g, int scheme,
-    int precision, double wscale, void *m0, void *m1) {
-  if (!n) return 0;
-  const bool do_sort = c->opt_sort && n >= (size_t) c->opt_sort_min;
+// One device-resident chunk: counting sort by mesh row, then the scatter.
+// `consumed` (optional) is recorded once the source buffer is no longer read.
+int sort_assign_chunk(psb_context *c, const double *src, size_t len, const AssignGeom &g,
+    int scheme, int precision, double wscale, void *m0, void *m1, cudaEvent_t consumed) {
+  if (!len) return 0;
+  const bool do_sort = c->opt_sort && len >= (size_t) c->opt_sort_min;
   if (!do_sort) {
     StageScope sc(c, PSB_T_ASSIGN, c->st);
     c->launches++;
-    return launch_assign(dev, n, g, scheme, precision, wscale, m0, m1, c->st);
+    if (launch_assign(src, len, g, scheme, precision, wscale, m0, m1, c->st)) return -1;
+    if (consumed) PSB_CUDA(cudaEventRecord(consumed, c->st));
+    return 0;
   }
-  const size_t CH = (size_t) 1 << 28;   // particles per chunk (8.6 GB of records)
-  const size_t nrow = (size_t) g.ng * g.ng;
-  const size_t chunk_max = std::min(n, CH);
-  if (c->keys.reserve(chunk_max * 4) || c->sorted.reserve(chunk_max * 32) ||
+  const size_t nrow = row_key_count(g);
+  if (nrow > 0x7fffffffull) { set_error("GRID_SIZE too large for the row sort\n"); return -1; }
+  if (c->keys.reserve(len * 4) || c->sorted.reserve(len * 32) ||
       c->hist.reserve(nrow * 4) || c->cursor.reserve(nrow * 4))
     return -1;
   size_t tmp_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->hist.as<uint32_t>(),
       c->cursor.as<uint32_t>(), (int) nrow, c->st);
   if (c->cubtmp.reserve(tmp_bytes)) return -1;
-  for (size_t off = 0; off < n; off += CH) {
-    const size_t len = std::min(CH, n - off);
-    const double *src = dev + 4 * off;
-    {
-      StageScope sc(c, PSB_T_SORT, c->st);
-      PSB_CUDA(cudaMemsetAsync(c->hist.p, 0, nrow * 4, c->st));
-      if (launch_row_keys(src, len, g, c->keys.as<uint32_t>(), c->hist.as<uint32_t>(), c->st))
-        return -1;
-      PSB_CUDA(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp_bytes, c->hist.as<uint32_t>(),
-          c->cursor.as<uint32_t>(), (int) nrow, c->st));
-      if (launch_row_scatter(src, len, c->keys.as<uint32_t>(), c->cursor.as<uint32_t>(),
-            c->sorted.as<double>(), c->st))
-        return -1;
-      c->launches += 5;
-    }
-    StageScope sc(c, PSB_T_ASSIGN, c->st);
-    if (launch_assign(c->sorted.as<double>(), len, g, scheme, precision, wscale, m0, m1, c->st))
+  {
+    StageScope sc(c, PSB_T_SORT, c->st);
+    PSB_CUDA(cudaMemsetAsync(c->hist.p, 0, nrow * 4, c->st));
+    if (launch_row_keys(src, len, g, c->keys.as<uint32_t>(), c->hist.as<uint32_t>(), c->st))
       return -1;
-    c->launches++;
+    PSB_CUDA(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp_bytes, c->hist.as<uint32_t>(),
+        c->cursor.as<uint32_t>(), (int) nrow, c->st));
+    if (launch_row_scatter(src, len, c->keys.as<uint32_t>(), c->cursor.as<uint32_t>(),
+          c->sorted.as<double>(), c->st))
+      return -1;
+    c->launches += 5;
   }
+  if (consumed) PSB_CUDA(cudaEventRecord(consumed, c->st));
+  StageScope sc(c, PSB_T_ASSIGN, c->st);
+  if (launch_assign(c->sorted.as<double>(), len, g, scheme, precision, wscale, m0, m1, c->st))
+    return -1;
+  c->launches++;
+  return 0;
+}
+
+// A catalogue that is already on the device.  Chunked so that 32-bit offsets
+// suffice and the sort scratch stays bounded.
+int assign_catalog(psb_context *c, const double *dev, size_t n, const AssignGeom &g, int scheme,
+    int precision, double wscale, void *m0, void *m1) {
+  const size_t CH = (size_t) 1 << 28;   // particles per chunk (8.6 GB of records)
+  for (size_t off = 0; off < n; off += CH)
+    if (sort_assign_chunk(c, dev + 4 * off, std::min(CH, n - off), g, scheme, precision, wscale,
+          m0, m1, nullptr))
+      return -1;
+  return 0;
+}
+
+// Copy `bytes` from host memory into a device buffer on the copy stream.
+// Pinned sources go straight to the copy engine; pageable ones are staged
+// through two pinned buffers filled by a few host threads, so the PCIe transfer
+// is not bound by one memcpy thread.
+int h2d_async(psb_context *c, void *dst, const void *src, size_t bytes, bool pinned,
+    cudaStream_t stream) {
+  if (!bytes) return 0;
+  if (pinned) {
+    PSB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
+    return 0;
+  }
+  const size_t CH = (size_t) 64 << 20;
+  if (!c->pinned[0]) {
+    for (int i = 0; i < 2; i++) {
+      PSB_CUDA(cudaHostAlloc(&c->pinned[i], CH, cudaHostAllocDefault));
+      PSB_CUDA(cudaEventCreateWithFlags(&c->pinned_free[i], cudaEventDisableTiming));
+    }
+    c->pinned_bytes = CH;
+  }
+  unsigned hw = std::thread::hardware_concurrency();
+  const int nthr = (int) std::max(1u, std::min(8u, hw ? hw : 1u));
+  size_t off = 0;
+  int slot = 0;
+  while (off < bytes) {
+    const size_t len = std::min(CH, bytes - off);
+    PSB_CUDA(cudaEventSynchronize(c->pinned_free[slot]));
+    char *stage = static_cast<char *>(c->pinned[slot]);
+    const char *from = static_cast<const char *>(src) + off;
+    if (nthr == 1 || len < ((size_t) 4 << 20)) memcpy(stage, from, len);
+    else {
+      std::vector<std::thread> th;
+      const size_t per = (len / nthr + 4095) & ~(size_t) 4095;
+      for (int t = 0; t < nthr; t++) {
+        const size_t a = std::min(len, per * t), b = std::min(len, per * (t + 1));
+        if (b > a) th.emplace_back([=] { memcpy(stage + a, from + a, b - a); });
+      }
+      for (auto &t : th) t.join();
+    }
+    PSB_CUDA(cudaMemcpyAsync(static_cast<char *>(dst) + off, stage, len,
+        cudaMemcpyHostToDevice, stream));
+    PSB_CUDA(cudaEventRecord(c->pinned_free[slot], stream));
+    off += len;
+    slot ^= 1;
+  }
+  return 0;
+}
+
+bool is_pinned(const void *p) {
+  cudaPointerAttributes at;
+  bool pinned = false;
+  if (cudaPointerGetAttributes(&at, p) == cudaSuccess)
+    pinned = (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged);
+  cudaGetLastError();
+  return pinned;
+}
+
+// A catalogue in HOST memory, box known in advance (simulation boxes): chunks
+// are uploaded on the copy stream while the previous chunk is being sorted and
+// scattered, so PCIe and the SMs work concurrently and the catalogue never has
+// to be resident as a whole.  Bounds partials of every chunk are appended to
+// c->bounds_host (reduced by the caller after the stream has drained).
+int stream_catalog(psb_context *c, const double *host, size_t n, const AssignGeom &g, int scheme,
+    int precision, double wscale, void *m0, void *m1) {
+  if (!n) return 0;
+  const size_t CH = (size_t) std::max<long>(c->opt_stream_chunk, 1 << 16);
+  const size_t chunk_max = std::min(n, CH);
+  const int nblk = c->sms * 8;
+  const size_t nchunk = (n + CH - 1) / CH;
+  if (c->bounds_part.reserve(sizeof(double) * 6 * nblk * nchunk)) return -1;
+  const bool pinned = is_pinned(host);
+  for (int s = 0; s < 2; s++) {
+    if (nchunk > (size_t) s && c->chunkbuf[s].reserve(chunk_max * 32)) return -1;
+    if (!c->ev_filled[s]) {
+      PSB_CUDA(cudaEventCreateWithFlags(&c->ev_filled[s], cudaEventDisableTiming));
+      PSB_CUDA(cudaEventCreateWithFlags(&c->ev_consumed[s], cudaEventDisableTiming));
+    }
+  }
+  // whatever ran on the compute stream before (a previous run) must be done
+  // with the chunk buffers
+  PSB_CUDA(cudaEventRecord(c->ev_consumed[0], c->st));
+  PSB_CUDA(cudaEventRecord(c->ev_consumed[1], c->st));
+  size_t k = 0;
+  for (size_t off = 0; off < n; off += CH, k++) {
+    const size_t len = std::min(CH, n - off);
+    const int s = (int) (k & 1);
+    double *buf = c->chunkbuf[s].as<double>();
+    PSB_CUDA(cudaStreamWaitEvent(c->st_copy, c->ev_consumed[s], 0));
+    {
+      StageScope sc(c, PSB_T_H2D, c->st_copy);
+      if (h2d_async(c, buf, host + 4 * off, len * 32, pinned, c->st_copy)) return -1;
+    }
+    PSB_CUDA(cudaEventRecord(c->ev_filled[s], c->st_copy));
+    PSB_CUDA(cudaStreamWaitEvent(c->st, c->ev_filled[s], 0));
+    {
+      StageScope sc(c, PSB_T_BOUNDS, c->st);
+      if (launch_bounds(buf, len, c->bounds_part.as<double>() + 6 * (size_t) nblk * k, nblk, c->st))
+        return -1;
+      c->launches++;
+    }
+    if (sort_assign_chunk(c, buf, len, g, scheme, precision, wscale, m0, m1, c->ev_consumed[s]))
+      return -1;
+  }
+  const size_t cur = c->bounds_host.size();
+  c->bounds_host.resize(cur + 6 * (size_t) nblk * nchunk);
+  PSB_CUDA(cudaMemcpyAsync(c->bounds_host.data() + cur, c->bounds_part.p,
+      sizeof(double) * 6 * nblk * nchunk, cudaMemcpyDeviceToHost, c->st));
+  // bounds_part is reused by the next catalogue: drain before returning
+  PSB_CUDA(cudaStreamSynchronize(c->st));
   return 0;
 }
 
@@ -502,6 +595,7 @@ psb_context *psb_create(int device) {
   cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, device);
   if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->st_geom, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_geom, cudaEventDisableTiming) != cudaSuccess) {
     set_error("failed to create CUDA streams\n");
     delete c;
@@ -522,7 +616,11 @@ void psb_destroy(psb_context *c) {
     c->fkl[i].release(); c->fk0copy[i].release();
     if (c->pinned[i]) cudaFreeHost(c->pinned[i]);
     if (c->pinned_free[i]) cudaEventDestroy(c->pinned_free[i]);
+    c->chunkbuf[i].release();
+    if (c->ev_filled[i]) cudaEventDestroy(c->ev_filled[i]);
+    if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]);
   }
+  if (c->st_copy) cudaStreamDestroy(c->st_copy);
   c->fka.release(); c->sorted.release(); c->keys.release(); c->hist.release();
   c->cursor.release(); c->cubtmp.release(); c->bounds_part.release(); c->fftwork.release();
   c->tables.release(); c->binscratch.release(); c->bins.release();
@@ -538,6 +636,10 @@ int psb_set_option(psb_context *c, const char *name, long value) {
   if (!c || !name) return -1;
   if (!strcmp(name, "sort")) { c->opt_sort = value; return 0; }
   if (!strcmp(name, "sort_min")) { c->opt_sort_min = value; return 0; }
+  if (!strcmp(name, "strip")) { c->opt_strip = value; return 0; }
+  if (!strcmp(name, "geom_sym")) { c->opt_geom_sym = value; return 0; }
+  if (!strcmp(name, "stream")) { c->opt_stream = value; return 0; }
+  if (!strcmp(name, "stream_chunk")) { c->opt_stream_chunk = value; return 0; }
   set_error("unknown option: %s\n", name);
   return -1;
 }
@@ -556,7 +658,12 @@ int psb_mesh(psb_context *c, const psb_params *par, const psb_cats *cats) {
   const int ngk = ng / 2 + 1, rowlen = 2 * ngk;
   const size_t mesh_bytes = (size_t) ng * ng * rowlen * prec;
 
-  // particles to the device (if they are not there already) + bounds
+  // Simulation boxes know their box before seeing a particle (min = 0, size =
+  // BOX_SIZE), so a host catalogue can be streamed: upload, bounds, sort and
+  // scatter chunk by chunk with PCIe and SMs overlapped; the bounds check of
+  // def_box is evaluated once the stream has drained.  Surveys need the bounds
+  // of every catalogue to define the box, so they are made resident first.
+  const bool streaming = par->issim && cats->memspace == PSB_MEM_HOST && c->opt_stream;
   const double *dptr[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
   size_t cnt[2][2] = {{0, 0}, {0, 0}};
   double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
@@ -566,6 +673,7 @@ int psb_mesh(psb_context *c, const psb_params *par, const psb_cats *cats) {
       const size_t n = s ? cats->nrand[i] : cats->ndata[i];
       cnt[i][s] = n;
       if (n && !src) { set_error("catalogs not read\n"); return -1; }
+      if (streaming) continue;
       if (cats->memspace == PSB_MEM_DEVICE) dptr[i][s] = src;
       else {
         if (upload(c, src, n, c->part_in[i][s])) return -1;
@@ -573,12 +681,19 @@ int psb_mesh(psb_context *c, const psb_params *par, const psb_cats *cats) {
       }
       if (coordinate_bounds(c, dptr[i][s], n, lo, hi)) return -1;
     }
-  for (int a = 0; a < 3; a++) c->bmax[a] = hi[a];
-  if (define_box(par, lo, hi, c->bmin, c->bsize)) return -1;
+  if (streaming) {
+    for (int a = 0; a < 3; a++) { c->bmin[a] = 0; c->bsize[a] = par->bsize[a]; }
+    c->bounds_host.clear();
+  }
+  else {
+    for (int a = 0; a < 3; a++) c->bmax[a] = hi[a];
+    if (define_box(par, lo, hi, c->bmin, c->bsize)) return -1;
+  }
 
   AssignGeom g;
   memset(&g, 0, sizeof g);
-  g.ng = ng; g.rowlen = rowlen; g.nxloc = ng;
+  g.ng = ng; g.rowlen = rowlen;
+  g.strip = (int) std::min<long>(std::max<long>(c->opt_strip, 1), ng);
   for (int a = 0; a < 3; a++) {
     g.org[a] = c->bmin[a];
     g.len[a] = c->bsize[a];
@@ -596,10 +711,15 @@ int psb_mesh(psb_context *c, const psb_params *par, const psb_cats *cats) {
       PSB_CUDA(cudaMemsetAsync(c->mesh[i][f].p, 0, mesh_bytes, c->st));
     }
     void *m0 = c->mesh[i][0].p, *m1 = par->intlace ? c->mesh[i][1].p : nullptr;
-    if (assign_catalog(c, dptr[i][0], cnt[i][0], g, par->assign, prec, 1.0, m0, m1)) return -1;
-    if (!par->issim &&
-        assign_catalog(c, dptr[i][1], cnt[i][1], g, par->assign, prec, -cats->alpha[i], m0, m1))
-      return -1;
+    if (streaming) {
+      if (stream_catalog(c, cats->data[i], cnt[i][0], g, par->assign, prec, 1.0, m0, m1)) return -1;
+    }
+    else {
+      if (assign_catalog(c, dptr[i][0], cnt[i][0], g, par->assign, prec, 1.0, m0, m1)) return -1;
+      if (!par->issim &&
+          assign_catalog(c, dptr[i][1], cnt[i][1], g, par->assign, prec, -cats->alpha[i], m0, m1))
+        return -1;
+    }
     if (par->issim) {           // src/genr_mesh.c:904-909
       const double vol = c->bsize[0] * c->bsize[1] * c->bsize[2];
       c->shot[i] = vol / cats->wdata[i];
@@ -611,6 +731,17 @@ int psb_mesh(psb_context *c, const psb_params *par, const psb_cats *cats) {
       if (nc == 2) printf("  Density field generated with %s for catalog %d\n", names[par->assign], i);
       else printf("  Density field generated with %s for the catalog\n", names[par->assign]);
     }
+  }
+  if (streaming) {
+    // def_box's checks (src/genr_mesh.c:516-531), after the fact
+    for (size_t q = 0; q + 5 < c->bounds_host.size(); q += 6)
+      for (int a = 0; a < 3; a++) {
+        lo[a] = std::min(lo[a], c->bounds_host[q + a]);
+        hi[a] = std::max(hi[a], c->bounds_host[q + 3 + a]);
+      }
+    for (int a = 0; a < 3; a++) c->bmax[a] = hi[a];
+    double bmin_chk[3], bsize_chk[3];
+    if (define_box(par, lo, hi, bmin_chk, bsize_chk)) return -1;
   }
   c->mesh_ready = true;
   return 0;
@@ -720,6 +851,8 @@ psb_result *psb_power(psb_context *c, const psb_params *par) {
   for (int i = 0; i < nl; i++) bg.poles[i] = par->poles[i];
   bg.issim = issim; bg.logk = par->logscale; bg.intlace = il;
   bg.y0 = 0; bg.nyloc = ng;
+  bg.symx = c->opt_geom_sym && (!issim || par->los[0] == 0.0);
+  bg.symy = c->opt_geom_sym && (!issim || par->los[1] == 0.0);
   for (int a = 0; a < 3; a++) {
     bg.los[a] = issim ? par->los[a] : 0.0;
     const double *base = c->tables.as<double>();

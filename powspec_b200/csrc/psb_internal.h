@@ -31,9 +31,7 @@ const char *get_error();
 struct AssignGeom {
   int ng;               // cells per side
   int rowlen;           // reals per z-row of the (padded, in-place FFT) mesh
-  int x0;               // first x-plane held locally (slab decomposition)
-  int nxloc;            // number of local x-planes incl. halo planes
-  int xhalo_lo;         // halo planes below x0 (wrapped)
+  int strip;            // rows per strip of the sort order (row-key layout)
   double org[3];        // lower box corner (MESH.min)
   double sorg[3];       // corner of the half-cell shifted box (MESH.smin)
   double len[3];        // box size
@@ -42,6 +40,8 @@ struct AssignGeom {
 // launch wrappers (assign.cu).  All asynchronous on `st`; return 0 / -1.
 int launch_bounds(const double *p, size_t n, double *partials /*[nblk*6]*/,
     int nblk, cudaStream_t st);
+// number of distinct sort keys for this geometry
+size_t row_key_count(const AssignGeom &g);
 int launch_row_keys(const double *p, size_t n, const AssignGeom &g,
     uint32_t *keys, uint32_t *hist, cudaStream_t st);
 int launch_row_scatter(const double *p, size_t n, const uint32_t *keys,
@@ -61,6 +61,7 @@ struct BinGeom {
   int poles[8];
   int issim, logk, intlace;
   int y0, nyloc;        // local range of the slowest index of the k-space array
+  int symx, symy;       // mode counting may fold n_x / n_y (los component is zero)
   double los[3];
   double k0;            // kedge[0]
   double k1;            // kedge[nbin]
