@@ -168,6 +168,7 @@ def main():
     ap.add_argument("--kind", type=int, default=0, help="0 uniform, 1 clustered catalogue")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="context option name=value (ablations)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -224,6 +225,11 @@ def main():
         torch.cuda.synchronize()
 
     ctx = powspec_b200.Context(local_rank)
+    for kv in args.opt:
+        name, val = kv.split("=")
+        ctx.set_option(name, int(val))
+    if args.opt:
+        config["options"] = args.opt
     n = w["npart"]
     conf = Conf(ndata=1, issim=True, bsize=(w["box"],) * 3, gsize=w["ng"],
                 assign=powspec_b200.powspec_assign_names.index(w["assign"]), intlace=w["interlace"],

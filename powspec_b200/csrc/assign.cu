@@ -244,13 +244,165 @@ __global__ void __launch_bounds__(256) k_assign(const double2 *__restrict__ p, s
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// z-coalesced scatter.  The cells a particle touches along z are contiguous in
+// memory (8..32 bytes), but with one particle per thread every lane of a RED
+// instruction hits a different mesh row, i.e. 32 L2 sector requests per
+// instruction — and the L2 tag/request rate, not HBM, bounds the kernel (ncu:
+// lts__t_tag_requests ~72 % of peak, DRAM traffic at the algorithmic minimum).
+// Here NZ = SCHEME+1 adjacent lanes share a particle, one z-cell each, so the
+// L1 merges them into one or two sector requests: the L2 request count drops
+// 1.6x (CIC), 2x (TSC), 2.3x (PCS).  The x/y stencils are recomputed by each of
+// the NZ lanes; to keep that redundancy cheap the coordinate transform avoids
+// the XU pipe: the division by the (constant) box size is a Markstein
+// reciprocal-FMA sequence, floor/int conversion a magic-number add.  Both are
+// re-done with the exact IEEE division whenever the fractional part is within
+// 1e-9 of a value that decides a cell (0, 1/2, 1), so the cell a particle lands
+// in is always the reference's.
+// ---------------------------------------------------------------------------
+struct AxisXform { double org, ng, len, inv_len; };
+
+__device__ __forceinline__ void split_floor(double t, int &c, double &d) {
+  const double MAGIC = 6755399441055744.0;      // 1.5 * 2^52: integer part lands in the low word
+  const double tm = __dadd_rn(t, MAGIC);
+  c = __double2loint(tm);
+  double r = __dsub_rn(tm, MAGIC);
+  if (r > t) { r -= 1.0; c -= 1; }
+  d = t - r;                                    // exact
+}
+
+__device__ __forceinline__ void grid_split(double x, const AxisXform &ax, int &c, double &d) {
+  const double a = __dmul_rn(__dsub_rn(x, ax.org), ax.ng);
+  // a / len, correctly rounded in all but pathological cases (Markstein)
+  const double q0 = a * ax.inv_len;
+  const double e = __fma_rn(-q0, ax.len, a);
+  double t = __fma_rn(e, ax.inv_len, q0);
+  split_floor(t, c, d);
+  if (d < 1e-9 || d > 1.0 - 1e-9 || fabs(d - 0.5) < 1e-9) {
+    t = __ddiv_rn(a, ax.len);                   // the reference's own arithmetic
+    c = (int) t;
+    d = t - (double) c;
+  }
+}
+
+// stencil from (base cell, fraction); same formulas as axis_stencil()
+template <int SCHEME>
+__device__ __forceinline__ void stencil_from(int c, double d, int ng, int (&idx)[SCHEME + 1],
+    double (&w)[SCHEME + 1]) {
+  if (c >= ng) c -= ng;         // quirk Q8 guard
+  if (c < 0) c = 0;
+  if constexpr (SCHEME == 0) {
+    if (d >= 0.5) c = wrap_up(c, ng);
+    idx[0] = c; w[0] = 1.0;
+  }
+  else if constexpr (SCHEME == 1) {
+    idx[0] = c; idx[1] = wrap_up(c, ng);
+    w[1] = d; w[0] = 1.0 - d;
+  }
+  else if constexpr (SCHEME == 2) {
+    double h;
+    if (d < 0.5) {
+      idx[1] = c; idx[0] = wrap_dn(c, ng); idx[2] = wrap_up(c, ng);
+      h = 0.5 - d;
+    }
+    else {
+      idx[0] = c; idx[1] = wrap_up(c, ng); idx[2] = wrap_up(idx[1], ng);
+      d = 1.0 - d;
+      h = 0.5 + d;
+    }
+    w[0] = h * (h * 0.5);
+    w[1] = 0.75 - d * d;
+    w[2] = 1.0 - w[0] - w[1];
+  }
+  else {
+    idx[1] = c; idx[0] = wrap_dn(c, ng); idx[2] = wrap_up(c, ng);
+    idx[3] = wrap_up(idx[2], ng);
+    double d2 = d * d;
+    w[3] = d2 * d;
+    w[2] = 1.0 + 3.0 * (d + d2 - w[3]);
+    w[1] = 4.0 - 6.0 * d2 + 3.0 * w[3];
+    w[0] = 6.0 - w[1] - w[2] - w[3];
+  }
+}
+
+template <int SCHEME, typename real>
+__device__ __forceinline__ void scatter_coop(const double x[3], double pw, const double org[3],
+    const AssignGeom &g, int zsel, real *__restrict__ mesh) {
+  constexpr int NS = SCHEME + 1;
+  int ix[NS], iy[NS], iz[NS];
+  double wx[NS], wy[NS], wz[NS];
+  int c; double d;
+  const double ngd = (double) g.ng;
+  grid_split(x[0], AxisXform{org[0], ngd, g.len[0], g.inv_len[0]}, c, d);
+  stencil_from<SCHEME>(c, d, g.ng, ix, wx);
+  grid_split(x[1], AxisXform{org[1], ngd, g.len[1], g.inv_len[1]}, c, d);
+  stencil_from<SCHEME>(c, d, g.ng, iy, wy);
+  grid_split(x[2], AxisXform{org[2], ngd, g.len[2], g.inv_len[2]}, c, d);
+  stencil_from<SCHEME>(c, d, g.ng, iz, wz);
+  // this lane's z-cell (compile-time unrolled select: no dynamic register indexing)
+  int izc = iz[0];
+  double wzc = wz[0];
+#pragma unroll
+  for (int q = 1; q < NS; q++)
+    if (zsel == q) { izc = iz[q]; wzc = wz[q]; }
+  if constexpr (SCHEME == 3) pw *= 0x1.2f684bda12f68p-8;
+#pragma unroll
+  for (int a = 0; a < NS; a++) wx[a] *= pw;
+#pragma unroll
+  for (int a = 0; a < NS; a++) {
+#pragma unroll
+    for (int b = 0; b < NS; b++) {
+      real *row = mesh + ((size_t) ix[a] * g.ng + iy[b]) * g.rowlen;
+      red_add(row + izc, (wx[a] * wy[b]) * wzc);
+    }
+  }
+}
+
+template <int SCHEME, typename real, bool INTERLACE>
+__global__ void __launch_bounds__(256) k_assign_coop(const double2 *__restrict__ p, size_t n,
+    AssignGeom g, double wscale, real *__restrict__ mesh0, real *__restrict__ mesh1) {
+  constexpr int NZ = SCHEME + 1;
+  constexpr int PPW = 32 / NZ;                  // particles per warp
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / NZ, zsel = lane - sub * NZ;
+  const size_t warp = blockIdx.x * (size_t) (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const size_t i = warp * PPW + sub;
+  if (sub < PPW && i < n) {
+    // the NZ lanes of a particle load the same 32 bytes: one broadcast request
+    double2 a = __ldg(p + 2 * i), b = __ldg(p + 2 * i + 1);
+    double x[3] = {a.x, a.y, b.x};
+    const double pw = b.y * wscale;
+    scatter_coop<SCHEME, real>(x, pw, g.org, g, zsel, mesh0);
+    if constexpr (INTERLACE) {
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+        if (x[k] >= __dadd_rn(g.sorg[k], g.len[k])) x[k] = __dsub_rn(x[k], g.len[k]);
+      scatter_coop<SCHEME, real>(x, pw, g.sorg, g, zsel, mesh1);
+    }
+  }
+}
+
 template <int SCHEME, typename real>
 static int launch_assign_t(const double *p, size_t n, const AssignGeom &g, double wscale,
     void *m0, void *m1, cudaStream_t st) {
+  const double2 *pp = reinterpret_cast<const double2 *>(p);
+  if (g.coop && SCHEME > 0) {
+    constexpr int PPB = 8 * (32 / (SCHEME + 1));        // particles per 256-thread block
+    const size_t nb = (n + PPB - 1) / PPB;
+    if (nb > 0x7fffffffull) { set_error("too many particles in one assignment chunk\n"); return -1; }
+    if (m1)
+      k_assign_coop<SCHEME, real, true><<<(int) nb, 256, 0, st>>>(pp, n, g, wscale,
+          static_cast<real *>(m0), static_cast<real *>(m1));
+    else
+      k_assign_coop<SCHEME, real, false><<<(int) nb, 256, 0, st>>>(pp, n, g, wscale,
+          static_cast<real *>(m0), nullptr);
+    PSB_CUDA(cudaGetLastError());
+    return 0;
+  }
   const size_t nblk = (n + 255) / 256;
   if (nblk > 0x7fffffffull) { set_error("too many particles in one assignment chunk\n"); return -1; }
   const int grid = (int) nblk;
-  const double2 *pp = reinterpret_cast<const double2 *>(p);
   if (m1)
     k_assign<SCHEME, real, true><<<grid, 256, 0, st>>>(pp, n, g, wscale,
         static_cast<real *>(m0), static_cast<real *>(m1));

@@ -38,6 +38,7 @@ namespace psb {
 // errors
 // ---------------------------------------------------------------------------
 static thread_local char g_err[1024] = "";
+static thread_local bool g_quiet = false;       // record the message but do not print it
 
 void set_error(const char *fmt, ...) {
   va_list ap;
@@ -45,8 +46,12 @@ void set_error(const char *fmt, ...) {
   vsnprintf(g_err, sizeof g_err, fmt, ap);
   va_end(ap);
   // the reference's P_ERR format, src/define.h:102,129
-  fprintf(stderr, "\n\x1B[31;1mError:\x1B[0m %s", g_err);
+  if (!g_quiet) fprintf(stderr, "\n\x1B[31;1mError:\x1B[0m %s", g_err);
 }
+struct QuietErrors {
+  QuietErrors() { g_quiet = true; }
+  ~QuietErrors() { g_quiet = false; }
+};
 const char *get_error() { return g_err; }
 
 static const double PI = 0x1.921fb54442d18p+1;  // src/define.h:37
@@ -130,6 +135,7 @@ struct psb_context {
   long opt_sort = 1;
   long opt_sort_min = 1 << 16;
   long opt_geom_sym = 1;                // fold +-n_x, +-n_y in the mode-counting pass
+  long opt_coop = 1;                    // z-coalesced scatter kernel
   long opt_strip = 64;                  // rows per strip of the sort order
   long opt_stream = 1;                  // overlap H2D with assignment for host catalogues (sims)
   long opt_stream_chunk = 1 << 24;      // particles per streamed chunk (512 MiB)
@@ -139,6 +145,15 @@ struct psb_context {
   psb_params par;
   double bmin[3], bsize[3], bmax[3];
   double shot[2], norm[2];
+
+  // k-bins, per-axis tables and mode counts prepared ahead of the FFTs
+  bool bins_ready = false;
+  psb_params bins_par;
+  double bins_box[3];
+  int nbin = 0;
+  std::vector<double> kedge;
+  BinGeom bg;
+  size_t bin_sb = 0;
 
   // timings
   std::vector<Interval> intervals;
@@ -567,6 +582,124 @@ int fft_inverse(psb_context *c, void *mesh) {
   return 0;
 }
 
+
+// powspec_init (src/multipole.c:335-394) + the per-axis tables + powspec_precomp
+// (src/multipole.c:111-257).  Everything here is independent of the particles,
+// so psb_mesh launches it on the side stream before the scatter: the
+// compute-bound mode counting then overlaps the bandwidth-bound upload, sort and
+// memset instead of competing with the FFTs.
+bool same_bins(const psb_context *c, const psb_params *p) {
+  if (!c->bins_ready) return false;
+  const psb_params &q = c->bins_par;
+  if (p->gsize != q.gsize || p->logscale != q.logscale || p->npole != q.npole ||
+      p->issim != q.issim || p->intlace != q.intlace || p->assign != q.assign ||
+      p->kmin != q.kmin || p->kmax != q.kmax || p->kbin != q.kbin)
+    return false;
+  for (int i = 0; i < p->npole; i++) if (p->poles[i] != q.poles[i]) return false;
+  for (int a = 0; a < 3; a++)
+    if ((p->issim && p->los[a] != q.los[a]) || c->bins_box[a] != c->bsize[a]) return false;
+  return true;
+}
+
+int prepare_bins(psb_context *c, const psb_params *par) {
+  c->bins_ready = false;
+  const int ng = par->gsize, ngk = ng / 2 + 1, nl = par->npole;
+  const bool issim = par->issim, il = par->intlace;
+  double bmax = std::max(c->bsize[0], std::max(c->bsize[1], c->bsize[2]));
+  double kny = PI * ng / bmax;
+  if (par->logscale) kny = log10(kny);
+  double kmax = kny;
+  if (par->kmax > 0 && kmax > par->kmax) kmax = par->kmax;
+  const double nbf = round((kmax - par->kmin) / par->kbin);
+  if (nbf >= INT_MAX) {
+    set_error("too many wave number bins due to the small bin size: %.10lg\n", par->kbin);
+    return -1;
+  }
+  int nbin = (int) nbf;
+  if (par->kmin + par->kbin * nbin > kny) nbin -= 1;
+  if (nbin < 1) {
+    set_error("not enough k bins given the Nyquist frequency and the bin size: %.10lg\n", par->kbin);
+    return -1;
+  }
+  c->nbin = nbin;
+  c->kedge.resize(nbin + 1);
+  for (int i = 0; i <= nbin; i++) c->kedge[i] = par->kmin + par->kbin * i;
+
+  // per-axis tables: k, k^2, window, interlace phase (3 x 5 x ng) + k^2 edges
+  const size_t tlen = (size_t) ng;
+  std::vector<double> &T = c->host_tables;
+  T.assign(15 * tlen + nbin + 1, 0.0);
+  const double fac = PI / ng;
+  for (int a = 0; a < 3; a++) {
+    const double vec = 2 * PI / c->bsize[a];    // src/multipole.c:113
+    double *kax = &T[(0 + a) * tlen], *kax2 = &T[(3 + a) * tlen], *wax = &T[(6 + a) * tlen];
+    double *pc = &T[(9 + a) * tlen], *ps = &T[(12 + a) * tlen];
+    for (int i = 0; i < ng; i++) {
+      const double n = (i <= (ng >> 1)) ? i : i - ng;
+      wax[i] = window_axis(il, par->assign, n * fac);
+      const double k = n * vec;
+      kax[i] = k;
+      kax2[i] = k * k;
+      const double ph = fac * n;                // src/multipole.c:468-476
+      pc[i] = cos(ph);
+      ps[i] = sin(ph);
+    }
+  }
+  if (par->logscale) {
+    const double k0 = c->kedge[0], k1 = c->kedge[nbin], dk = par->kbin;
+    double *e = &T[15 * tlen];
+    for (int b = 0; b < nbin; b++)
+      e[b] = bisect_first([&](double x) {
+        const double kc = 0.5 * log10(x);
+        if (kc >= k1) return true;
+        return ref_log_bin(x, k0, k1, dk, nbin) >= b;
+      });
+    e[nbin] = bisect_first([&](double x) { return 0.5 * log10(x) >= k1; });
+  }
+  if (c->tables.reserve(T.size() * sizeof(double))) return -1;
+  BinGeom &bg = c->bg;
+  memset(&bg, 0, sizeof bg);
+  bg.ng = ng; bg.ngk = ngk; bg.nbin = nbin; bg.nl = nl;
+  for (int i = 0; i < nl; i++) bg.poles[i] = par->poles[i];
+  bg.issim = issim; bg.logk = par->logscale; bg.intlace = il;
+  bg.y0 = 0; bg.nyloc = ng;
+  bg.symx = c->opt_geom_sym && (!issim || par->los[0] == 0.0);
+  bg.symy = c->opt_geom_sym && (!issim || par->los[1] == 0.0);
+  for (int a = 0; a < 3; a++) {
+    bg.los[a] = issim ? par->los[a] : 0.0;
+    const double *base = c->tables.as<double>();
+    bg.kax[a] = base + (0 + a) * tlen; bg.kax2[a] = base + (3 + a) * tlen;
+    bg.wax[a] = base + (6 + a) * tlen;
+    bg.pc[a] = base + (9 + a) * tlen; bg.ps[a] = base + (12 + a) * tlen;
+  }
+  bg.k2edge = par->logscale ? c->tables.as<double>() + 15 * tlen : nullptr;
+  bg.k0 = c->kedge[0]; bg.k1 = c->kedge[nbin]; bg.dk = par->kbin;
+
+  const size_t nacc = (size_t) nl * nbin;
+  const size_t sb = bin_scratch_bytes(bg);
+  c->bin_sb = sb;
+  // device bins: cnt (u64) | km | lcnt[nl*nbin] | pl0 | pl1 | xpl
+  const size_t bins_doubles = 2 * (size_t) nbin + 4 * nacc;
+  if (c->binscratch.reserve(2 * sb) || c->bins.reserve(bins_doubles * sizeof(double))) return -1;
+  PSB_CUDA(cudaMemcpyAsync(c->tables.p, T.data(), T.size() * sizeof(double),
+      cudaMemcpyHostToDevice, c->st_geom));
+  PSB_CUDA(cudaMemsetAsync(c->bins.p, 0, bins_doubles * sizeof(double), c->st_geom));
+  unsigned long long *d_cnt = c->bins.as<unsigned long long>();
+  double *d_km = c->bins.as<double>() + nbin;
+  double *d_lcnt = d_km + nbin;
+  {
+    StageScope sc(c, PSB_T_GEOM, c->st_geom);
+    if (launch_geometry(bg, d_cnt, d_km, d_lcnt, c->binscratch.as<double>(), sb, c->st_geom))
+      return -1;
+    c->launches += 3;
+  }
+  PSB_CUDA(cudaEventRecord(c->ev_geom, c->st_geom));
+  c->bins_par = *par;
+  for (int a = 0; a < 3; a++) c->bins_box[a] = c->bsize[a];
+  c->bins_ready = true;
+  return 0;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------
@@ -637,6 +770,7 @@ int psb_set_option(psb_context *c, const char *name, long value) {
   if (!strcmp(name, "sort")) { c->opt_sort = value; return 0; }
   if (!strcmp(name, "sort_min")) { c->opt_sort_min = value; return 0; }
   if (!strcmp(name, "strip")) { c->opt_strip = value; return 0; }
+  if (!strcmp(name, "coop")) { c->opt_coop = value; return 0; }
   if (!strcmp(name, "geom_sym")) { c->opt_geom_sym = value; return 0; }
   if (!strcmp(name, "stream")) { c->opt_stream = value; return 0; }
   if (!strcmp(name, "stream_chunk")) { c->opt_stream_chunk = value; return 0; }
@@ -653,6 +787,7 @@ int psb_mesh(psb_context *c, const psb_params *par, const psb_cats *cats) {
   reset_timings(c);
   c->launches = 0;
   c->mesh_ready = false;
+  c->bins_ready = false;
   c->par = *par;
   const int nc = par->ncat, ng = par->gsize, prec = par->precision;
   const int ngk = ng / 2 + 1, rowlen = 2 * ngk;
@@ -689,14 +824,23 @@ int psb_mesh(psb_context *c, const psb_params *par, const psb_cats *cats) {
     for (int a = 0; a < 3; a++) c->bmax[a] = hi[a];
     if (define_box(par, lo, hi, c->bmin, c->bsize)) return -1;
   }
+  // the box is known: start the particle-independent part of powspec() now.  A
+  // failure here (e.g. no k bin below the Nyquist frequency) belongs to powspec()
+  // in the reference, so it is left for psb_power to report.
+  {
+    QuietErrors q;
+    prepare_bins(c, par);
+  }
 
   AssignGeom g;
   memset(&g, 0, sizeof g);
   g.ng = ng; g.rowlen = rowlen;
   g.strip = (int) std::min<long>(std::max<long>(c->opt_strip, 1), ng);
+  g.coop = (int) c->opt_coop;
   for (int a = 0; a < 3; a++) {
     g.org[a] = c->bmin[a];
     g.len[a] = c->bsize[a];
+    g.inv_len[a] = 1.0 / c->bsize[a];
     g.sorg[a] = c->bmin[a] - 0.5 * c->bsize[a] / ng;    // src/genr_mesh.c:817-818
   }
 
@@ -787,112 +931,29 @@ psb_result *psb_power(psb_context *c, const psb_params *par) {
   const size_t mesh_bytes = (size_t) ng * ng * 2 * ngk * prec;
   const size_t ntot = (size_t) ng * ng * ng;
 
-  // ---- powspec_init, src/multipole.c:335-394
-  double bmax = std::max(c->bsize[0], std::max(c->bsize[1], c->bsize[2]));
-  double kny = PI * ng / bmax;
-  if (par->logscale) kny = log10(kny);
-  double kmax = kny;
-  if (par->kmax > 0 && kmax > par->kmax) kmax = par->kmax;
-  const double nbf = round((kmax - par->kmin) / par->kbin);
-  if (nbf >= INT_MAX) {
-    set_error("too many wave number bins due to the small bin size: %.10lg\n", par->kbin);
-    return nullptr;
-  }
-  int nbin = (int) nbf;
-  if (par->kmin + par->kbin * nbin > kny) nbin -= 1;
-  if (nbin < 1) {
-    set_error("not enough k bins given the Nyquist frequency and the bin size: %.10lg\n", par->kbin);
-    return nullptr;
-  }
+  // ---- k-bins, tables and mode counts: normally already in flight since psb_mesh
+  if (!same_bins(c, par) && prepare_bins(c, par)) { c->mesh_ready = false; return nullptr; }
+  const int nbin = c->nbin;
+  const BinGeom &bg = c->bg;
+  const size_t sb = c->bin_sb;
   psb_result *res = new psb_result();
   res->nbin = nbin; res->nl = nl;
-  res->kedge.resize(nbin + 1); res->k.resize(nbin); res->km.assign(nbin, 0);
+  res->kedge = c->kedge; res->k.resize(nbin); res->km.assign(nbin, 0);
   res->cnt.assign(nbin, 0); res->lcnt.assign((size_t) nl * nbin, 0);
-  for (int i = 0; i <= nbin; i++) res->kedge[i] = par->kmin + par->kbin * i;
   for (int i = 0; i < nbin; i++) res->k[i] = (res->kedge[i] + res->kedge[i + 1]) * 0.5;
-  auto fail = [&]() { delete res; c->mesh_ready = false; return (psb_result *) nullptr; };
-
-  // ---- per-axis tables: k, k^2, window, interlace phase (3 x 5 x ng) + k^2 edges
-  const size_t tlen = (size_t) ng;
-  std::vector<double> &T = c->host_tables;
-  T.assign(15 * tlen + nbin + 1, 0.0);
-  const double fac = PI / ng;
-  for (int a = 0; a < 3; a++) {
-    const double vec = 2 * PI / c->bsize[a];    // src/multipole.c:113
-    double *kax = &T[(0 + a) * tlen], *kax2 = &T[(3 + a) * tlen], *wax = &T[(6 + a) * tlen];
-    double *pc = &T[(9 + a) * tlen], *ps = &T[(12 + a) * tlen];
-    for (int i = 0; i < ng; i++) {
-      const double n = (i <= (ng >> 1)) ? i : i - ng;
-      wax[i] = window_axis(il, c->par.assign, n * fac);
-      const double k = n * vec;
-      kax[i] = k;
-      kax2[i] = k * k;
-      const double ph = fac * n;                // src/multipole.c:468-476
-      pc[i] = cos(ph);
-      ps[i] = sin(ph);
-    }
-  }
-  if (par->logscale) {
-    const double k0 = res->kedge[0], k1 = res->kedge[nbin], dk = par->kbin;
-    double *e = &T[15 * tlen];
-    for (int b = 0; b < nbin; b++)
-      e[b] = bisect_first([&](double x) {
-        const double kc = 0.5 * log10(x);
-        if (kc >= k1) return true;
-        const int q = ref_log_bin(x, k0, k1, dk, nbin);
-        return q >= b;
-      });
-    e[nbin] = bisect_first([&](double x) { return 0.5 * log10(x) >= k1; });
-  }
-  if (c->tables.reserve(T.size() * sizeof(double))) return fail();
-  BinGeom bg;
-  memset(&bg, 0, sizeof bg);
-  bg.ng = ng; bg.ngk = ngk; bg.nbin = nbin; bg.nl = nl;
-  for (int i = 0; i < nl; i++) bg.poles[i] = par->poles[i];
-  bg.issim = issim; bg.logk = par->logscale; bg.intlace = il;
-  bg.y0 = 0; bg.nyloc = ng;
-  bg.symx = c->opt_geom_sym && (!issim || par->los[0] == 0.0);
-  bg.symy = c->opt_geom_sym && (!issim || par->los[1] == 0.0);
-  for (int a = 0; a < 3; a++) {
-    bg.los[a] = issim ? par->los[a] : 0.0;
-    const double *base = c->tables.as<double>();
-    bg.kax[a] = base + (0 + a) * tlen; bg.kax2[a] = base + (3 + a) * tlen;
-    bg.wax[a] = base + (6 + a) * tlen;
-    bg.pc[a] = base + (9 + a) * tlen; bg.ps[a] = base + (12 + a) * tlen;
-  }
-  bg.k2edge = par->logscale ? c->tables.as<double>() + 15 * tlen : nullptr;
-  bg.k0 = res->kedge[0]; bg.k1 = res->kedge[nbin]; bg.dk = par->kbin;
-
+  auto fail = [&]() { delete res; c->mesh_ready = false; c->bins_ready = false; return (psb_result *) nullptr; };
   const size_t nacc = (size_t) nl * nbin;
-  const size_t sb = bin_scratch_bytes(bg);
-  // device bins: cnt (u64) | km | lcnt[nl*nbin] | pl0 | pl1 | xpl
   const size_t bins_doubles = 2 * (size_t) nbin + 4 * nacc;
   auto hard = [&](cudaError_t e) {
     if (e != cudaSuccess) { set_error("CUDA failure: %s\n", cudaGetErrorString(e)); return true; }
     return false;
   };
-  if (c->binscratch.reserve(2 * sb) || c->bins.reserve(bins_doubles * sizeof(double))) return fail();
-  if (hard(cudaMemcpyAsync(c->tables.p, T.data(), T.size() * sizeof(double),
-          cudaMemcpyHostToDevice, c->st))) return fail();
-  if (hard(cudaMemsetAsync(c->bins.p, 0, bins_doubles * sizeof(double), c->st))) return fail();
-  unsigned long long *d_cnt = c->bins.as<unsigned long long>();
-  double *d_km = c->bins.as<double>() + nbin;
-  double *d_lcnt = d_km + nbin;
+  double *d_lcnt = c->bins.as<double>() + 2 * nbin;
   double *d_pl[2] = {d_lcnt + nacc, d_lcnt + 2 * nacc};
   double *d_xpl = d_lcnt + 3 * nacc;
-  double *scratch_geom = c->binscratch.as<double>();
   double *scratch_bin = reinterpret_cast<double *>(c->binscratch.as<char>() + sb);
-
-  // ---- powspec_precomp, src/multipole.c:111-257: pure geometry, own stream so it
-  // overlaps the FFTs
-  if (hard(cudaEventRecord(c->ev_geom, c->st)) ||
-      hard(cudaStreamWaitEvent(c->st_geom, c->ev_geom, 0))) return fail();
-  {
-    StageScope sc(c, PSB_T_GEOM, c->st_geom);
-    if (launch_geometry(bg, d_cnt, d_km, d_lcnt, scratch_geom, sb, c->st_geom)) return fail();
-    c->launches += 3;
-  }
-  if (hard(cudaEventRecord(c->ev_geom, c->st_geom))) return fail();
+  // the bins are zeroed and the tables uploaded on the side stream
+  if (hard(cudaStreamWaitEvent(c->st, c->ev_geom, 0))) return fail();
 
   // ---- dens_k0, src/multipole.c:435-505
   if (ensure_plans(c, ng, prec, need_ell && il)) return fail();
@@ -1024,7 +1085,6 @@ psb_result *psb_power(psb_context *c, const psb_params *par) {
   }
 
   // ---- results back: a few thousand doubles
-  if (hard(cudaStreamWaitEvent(c->st, c->ev_geom, 0))) return fail();
   std::vector<double> hb(bins_doubles);
   if (hard(cudaMemcpyAsync(hb.data(), c->bins.p, bins_doubles * sizeof(double),
           cudaMemcpyDeviceToHost, c->st)) || hard(cudaStreamSynchronize(c->st)))
@@ -1097,6 +1157,7 @@ psb_result *psb_power(psb_context *c, const psb_params *par) {
   for (int i = 0; i < 2; i++) { res->shot[i] = i < nc ? shot[i] : 0; res->norm[i] = i < nc ? norm[i] : 0; }
   for (int a = 0; a < 3; a++) { res->bmin[a] = c->bmin[a]; res->bsize[a] = c->bsize[a]; res->bmax[a] = c->bmax[a]; }
   c->mesh_ready = false;        // the FFTs ran in place: the meshes are consumed
+  c->bins_ready = false;
   c->ms[PSB_T_TOTAL] = 0;
   for (int s = 0; s < PSB_T_TOTAL; s++) c->ms[PSB_T_TOTAL] += c->ms[s];
   return res;

@@ -32,9 +32,11 @@ struct AssignGeom {
   int ng;               // cells per side
   int rowlen;           // reals per z-row of the (padded, in-place FFT) mesh
   int strip;            // rows per strip of the sort order (row-key layout)
+  int coop;             // z-coalesced scatter (NZ lanes per particle)
   double org[3];        // lower box corner (MESH.min)
   double sorg[3];       // corner of the half-cell shifted box (MESH.smin)
   double len[3];        // box size
+  double inv_len[3];    // RN(1 / len), for the division-free coordinate transform
 };
 
 // launch wrappers (assign.cu).  All asynchronous on `st`; return 0 / -1.

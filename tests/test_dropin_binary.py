@@ -1,0 +1,120 @@
+"""The seam, end to end: the reference's UNMODIFIED host program (main,
+load_conf, read_cata, cnvt_coord, save_res — compiled from /root/reference by
+`make -C oracle dropin`) linked against libpowspec_b200.so (POWSPEC_b200) must
+write the same output files as the same host linked with the reference's own
+genr_mesh.o + multipole.o (POWSPEC_ref): identical header and format, identical
+mode counts, P_ell within 1e-6.  Same powspec.conf form, same ASCII catalogues."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "POWSPEC_ref")
+OUR_BIN = os.path.join(ROOT, "oracle", "_ref", "POWSPEC_b200")
+
+
+def _need_binaries():
+    if not (os.path.exists(REF_BIN) and os.path.exists(OUR_BIN)):
+        pytest.skip("oracle/_ref/POWSPEC_{ref,b200} not built (needs /root/reference at build time)")
+
+
+def _run(binary, conf, extra, cwd, threads):
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+    p = subprocess.run([binary, "-c", conf, *extra], cwd=cwd, env=env, capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout + p.stderr
+    return p.stdout
+
+
+def _compare(fa, fb, ncols_int=(4,)):
+    la, lb = open(fa).read().splitlines(), open(fb).read().splitlines()
+    assert len(la) == len(lb)
+    rows_a, rows_b = [], []
+    for a, b in zip(la, lb):
+        if a.startswith("#"):
+            assert a == b, f"header differs:\n{a}\n{b}"
+        else:
+            rows_a.append([float(x) for x in a.split()])
+            rows_b.append([float(x) for x in b.split()])
+    A, B = np.array(rows_a), np.array(rows_b)
+    assert A.shape == B.shape and A.shape[0] > 0
+    assert np.array_equal(A[:, 4], B[:, 4]), "nmod differs"
+    assert np.allclose(A[:, :4], B[:, :4], rtol=1e-9, atol=0)
+    floor = 1e-3 * np.abs(A[:, 5:]).max()
+    err = np.abs(A[:, 5:] - B[:, 5:]) / np.maximum(np.abs(A[:, 5:]), floor)
+    # the files carry 10 significant digits (OFMT_DBL, src/define.h:107)
+    assert err.max() < 1e-6, err.max()
+
+
+def test_sim_auto_and_cross(tmp_path):
+    _need_binaries()
+    rng = np.random.default_rng(21)
+    for tag, n in (("a", 4000), ("b", 3000)):
+        np.savetxt(tmp_path / f"cat_{tag}.txt", np.c_[rng.random((n, 3)) * 200.0, rng.uniform(0.5, 2, n)],
+                   fmt="%.17g")
+    (tmp_path / "sim.conf").write_text("""
+DATA_CATALOG = [cat_a.txt, cat_b.txt]
+DATA_FORMATTER = ["%lf %lf %lf %lf", "%lf %lf %lf %lf"]
+DATA_POSITION = [$1,$2,$3,$1,$2,$3]
+DATA_WT_COMP = [$4, $4]
+CUBIC_SIM = T
+LINE_OF_SIGHT = [0,0,1]
+BOX_SIZE = 200
+GRID_SIZE = 32
+PARTICLE_ASSIGN = 3
+GRID_INTERLACE = T
+MULTIPOLE = [0,2,4]
+KMIN = 0
+BIN_SIZE = 0.05
+OVERWRITE = 1
+VERBOSE = F
+""")
+    _run(REF_BIN, "sim.conf", ["-a", "[ref_a.txt,ref_b.txt]", "-x", "ref_x.txt"], tmp_path, 4)
+    out = _run(OUR_BIN, "sim.conf", ["-a", "[our_a.txt,our_b.txt]", "-x", "our_x.txt"], tmp_path, 4)
+    assert "Generating meshes for FFT" in out and "Evaluating power spectra" in out
+    for t in ("a", "b", "x"):
+        _compare(tmp_path / f"ref_{t}.txt", tmp_path / f"our_{t}.txt")
+
+
+def test_survey_with_randoms_and_fkp(tmp_path):
+    _need_binaries()
+
+    def cat(seed, n):
+        r = np.random.default_rng(seed)
+        ra, dec = np.deg2rad(r.uniform(100, 160, n)), np.deg2rad(r.uniform(-10, 40, n))
+        d = r.uniform(800, 1500, n)
+        nz = np.full(n, 3e-4)
+        return np.c_[d * np.cos(dec) * np.cos(ra), d * np.cos(dec) * np.sin(ra), d * np.sin(dec),
+                     r.uniform(0.8, 1.2, n), 1 / (1 + 1e4 * nz), nz]
+    np.savetxt(tmp_path / "data.txt", cat(1, 3000), fmt="%.17g")
+    np.savetxt(tmp_path / "rand.txt", cat(2, 15000), fmt="%.17g")
+    (tmp_path / "survey.conf").write_text("""
+DATA_CATALOG = data.txt
+RAND_CATALOG = rand.txt
+DATA_FORMATTER = "%lf %lf %lf %lf %lf %lf"
+RAND_FORMATTER = "%lf %lf %lf %lf %lf %lf"
+DATA_POSITION = [$1,$2,$3]
+RAND_POSITION = [$1,$2,$3]
+DATA_WT_COMP = $4
+RAND_WT_COMP = $4
+DATA_WT_FKP = $5
+RAND_WT_FKP = $5
+DATA_NZ = $6
+RAND_NZ = $6
+CUBIC_SIM = F
+GRID_SIZE = 32
+PARTICLE_ASSIGN = 2
+GRID_INTERLACE = T
+MULTIPOLE = [0,2,4]
+KMIN = 0
+BIN_SIZE = 0.01
+OVERWRITE = 1
+VERBOSE = F
+""")
+    # one thread for the reference: its get_coord_bound races (see tests/test_oracle.py)
+    _run(REF_BIN, "survey.conf", ["-a", "ref.txt"], tmp_path, 1)
+    _run(OUR_BIN, "survey.conf", ["-a", "our.txt"], tmp_path, 4)
+    _compare(tmp_path / "ref.txt", tmp_path / "our.txt")
