@@ -359,26 +359,39 @@ __device__ __forceinline__ void scatter_coop(const double x[3], double pw, const
   }
 }
 
+constexpr int COOP_ITER = 1;    // particle groups per warp (4 was measured slower: 80 regs, lower occupancy)
+
 template <int SCHEME, typename real, bool INTERLACE>
 __global__ void __launch_bounds__(256) k_assign_coop(const double2 *__restrict__ p, size_t n,
     AssignGeom g, double wscale, real *__restrict__ mesh0, real *__restrict__ mesh1) {
   constexpr int NZ = SCHEME + 1;
-  constexpr int PPW = 32 / NZ;                  // particles per warp
+  constexpr int PPW = 32 / NZ;                  // particles per warp and iteration
   const int lane = threadIdx.x & 31;
   const int sub = lane / NZ, zsel = lane - sub * NZ;
   const size_t warp = blockIdx.x * (size_t) (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const size_t i = warp * PPW + sub;
-  if (sub < PPW && i < n) {
-    // the NZ lanes of a particle load the same 32 bytes: one broadcast request
-    double2 a = __ldg(p + 2 * i), b = __ldg(p + 2 * i + 1);
-    double x[3] = {a.x, a.y, b.x};
-    const double pw = b.y * wscale;
-    scatter_coop<SCHEME, real>(x, pw, g.org, g, zsel, mesh0);
-    if constexpr (INTERLACE) {
+  const size_t first = warp * (PPW * COOP_ITER) + sub;
+  // all loads of the warp's COOP_ITER groups are in flight before the first
+  // reduction is issued (the NZ lanes of a particle load the same 32 bytes: one
+  // broadcast request)
+  double2 a[COOP_ITER], b[COOP_ITER];
 #pragma unroll
-      for (int k = 0; k < 3; k++)
-        if (x[k] >= __dadd_rn(g.sorg[k], g.len[k])) x[k] = __dsub_rn(x[k], g.len[k]);
-      scatter_coop<SCHEME, real>(x, pw, g.sorg, g, zsel, mesh1);
+  for (int it = 0; it < COOP_ITER; it++) {
+    const size_t i = first + (size_t) it * PPW;
+    if (sub < PPW && i < n) { a[it] = __ldg(p + 2 * i); b[it] = __ldg(p + 2 * i + 1); }
+  }
+#pragma unroll
+  for (int it = 0; it < COOP_ITER; it++) {
+    const size_t i = first + (size_t) it * PPW;
+    if (sub < PPW && i < n) {
+      double x[3] = {a[it].x, a[it].y, b[it].x};
+      const double pw = b[it].y * wscale;
+      scatter_coop<SCHEME, real>(x, pw, g.org, g, zsel, mesh0);
+      if constexpr (INTERLACE) {
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+          if (x[k] >= __dadd_rn(g.sorg[k], g.len[k])) x[k] = __dsub_rn(x[k], g.len[k]);
+        scatter_coop<SCHEME, real>(x, pw, g.sorg, g, zsel, mesh1);
+      }
     }
   }
 }
@@ -388,7 +401,7 @@ static int launch_assign_t(const double *p, size_t n, const AssignGeom &g, doubl
     void *m0, void *m1, cudaStream_t st) {
   const double2 *pp = reinterpret_cast<const double2 *>(p);
   if (g.coop && SCHEME > 0) {
-    constexpr int PPB = 8 * (32 / (SCHEME + 1));        // particles per 256-thread block
+    constexpr int PPB = 8 * COOP_ITER * (32 / (SCHEME + 1));    // particles per 256-thread block
     const size_t nb = (n + PPB - 1) / PPB;
     if (nb > 0x7fffffffull) { set_error("too many particles in one assignment chunk\n"); return -1; }
     if (m1)

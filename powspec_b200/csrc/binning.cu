@@ -48,24 +48,24 @@ __device__ __forceinline__ double legendre(int ell, double x) {
   }
 }
 
-// Bin of a squared wavenumber, exactly as the reference evaluates it
-// (src/multipole.c:145-159): returns -1 for cells it marks unused (alias = 0).
-__device__ __forceinline__ int bin_of(const BinGeom &g, double k2, double &kmod) {
-  kmod = __dsqrt_rn(k2);
-  if (!g.logk) {
-    if (kmod < g.k0 || kmod >= g.k1) return -1;
-    int b = (int) __ddiv_rn(__dsub_rn(kmod, g.k0), g.dk);
-    return (b < 0 || b >= g.nbin) ? -1 : b;
-  }
-  // log bins: glibc's log10 decides in the reference.  The host has bisected,
-  // with libm, the smallest k^2 that lands in each bin (monotone expression);
-  // the device only needs a guess and two comparisons.
-  const double *e = g.k2edge;
-  if (!(k2 >= e[0]) || k2 >= e[g.nbin]) return -1;
-  int b = (int) ((0.5 * log10(k2) - g.k0) / g.dk);
+// Bin of a squared wavenumber.  The reference decides it with
+//   kmod = sqrt(k2) [or 0.5*log10(k2)];  unused if kmod < kedge[0] || kmod >= kedge[nbin];
+//   bin = (int) ((kmod - kedge[0]) / dk)              (src/multipole.c:145-159)
+// which is a monotone step function of k2.  The host bisects, with exactly those
+// operations (and glibc's log10 for log bins), the smallest double k2 that lands
+// in each bin; the device then only needs a cheap guess and two comparisons
+// against that table instead of an IEEE sqrt and division per cell — and the
+// result is the reference's bin by construction.  `edges` = nbin+1 thresholds
+// (shared memory); returns -1 for cells the reference marks unused (alias = 0).
+__device__ __forceinline__ int bin_of(const BinGeom &g, const double *edges, double k2,
+    double rk) {
+  if (!(k2 >= edges[0]) || k2 >= edges[g.nbin]) return -1;
+  // rk = 1/sqrt(k2) (or anything: the guess is corrected below)
+  const double kc = g.logk ? 0.5 * log10(k2) : k2 * rk;
+  int b = (int) ((kc - g.k0) * g.inv_dk);
   b = max(0, min(b, g.nbin - 1));
-  while (k2 < e[b]) b--;
-  while (k2 >= e[b + 1]) b++;
+  while (k2 < edges[b]) b--;
+  while (k2 >= edges[b + 1]) b++;
   return b;
 }
 
@@ -110,9 +110,12 @@ __global__ void __launch_bounds__(256) k_spectrum(BinGeom g, const void *__restr
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nwarp = blockDim.x >> 5;
   const int nacc = NV * g.nbin;
-  double *bins = smem + (size_t) warp * nacc;
+  // layout: [nbin+1 bin thresholds][nwarp x nacc warp-private bins]
+  double *edges = smem;
+  double *bins = smem + (g.nbin + 1) + (size_t) warp * nacc;
+  for (int q = threadIdx.x; q <= g.nbin; q += blockDim.x) edges[q] = g.k2edge[q];
   for (int q = lane; q < nacc; q += 32) bins[q] = 0.0;
-  __syncwarp();
+  __syncthreads();
 
   const bool cross = (Fb0 != Fa0);
   // The mode-counting pass is pure geometry: when the line of sight has no x
@@ -161,8 +164,8 @@ __global__ void __launch_bounds__(256) k_spectrum(BinGeom g, const void *__restr
           }
         }
         const double k2 = __dadd_rn(k2ij, __ldg(g.kax2[2] + k));
-        double kmod;
-        key = bin_of(g, k2, kmod);
+        const double rk = (k2 > 0.0) ? rsqrt(k2) : 0.0;
+        key = bin_of(g, edges, k2, rk);
         // sims skip the DC mode in the sums (src/multipole.c:806,939) but not
         // in the counts (quirk Q3)
         if (MODE == MODE_SIM && k2 == 0.0) key = -1;
@@ -188,12 +191,12 @@ __global__ void __launch_bounds__(256) k_spectrum(BinGeom g, const void *__restr
           }
           if (MODE == MODE_SURVEY) v[0] = p;
           else {
-            const double mu = (k2 == 0.0) ? 0.0
-                : __ddiv_rn(__dadd_rn(muij, __dmul_rn(__ldg(g.kax[2] + k), g.los[2])), kmod);
+            // mu = k.los / |k|  (src/multipole.c:812-813)
+            const double mu = __dadd_rn(muij, __dmul_rn(__ldg(g.kax[2] + k), g.los[2])) * rk;
             constexpr int L0 = (MODE == MODE_GEOM) ? 2 : 0;
             if (MODE == MODE_GEOM) {
               v[0] = mult;
-              v[1] = mult * (g.logk ? 0.0 : kmod);
+              v[1] = mult * (g.logk ? 0.0 : k2 * rk);   // |k|; overwritten for log bins (Q7)
             }
 #pragma unroll
             for (int l = 0; l < NV - L0; l++) {
@@ -217,7 +220,7 @@ __global__ void __launch_bounds__(256) k_spectrum(BinGeom g, const void *__restr
   double *out = partials + (size_t) blockIdx.x * nacc;
   for (int q = threadIdx.x; q < nacc; q += blockDim.x) {
     double s = 0.0;
-    for (int w = 0; w < nwarp; w++) s += smem[(size_t) w * nacc + q];
+    for (int w = 0; w < nwarp; w++) s += smem[(g.nbin + 1) + (size_t) w * nacc + q];
     out[q] = s;
   }
 }
@@ -245,13 +248,14 @@ __global__ void k_unpack_geometry(const double *__restrict__ acc, int nbin, int 
 struct LaunchShape { int blocks, threads; size_t smem; };
 
 template <typename K>
-int shape_for(K kernel, int nacc, LaunchShape &ls) {
-  // warp-private bins: nacc doubles per warp
+int shape_for(K kernel, int nacc, int nbin, LaunchShape &ls) {
+  // bin thresholds + warp-private bins (nacc doubles per warp)
   int threads = 256;
-  size_t smem = (size_t) nacc * sizeof(double) * (threads / 32);
+  auto bytes = [&](int t) { return ((size_t) nacc * (t / 32) + nbin + 1) * sizeof(double); };
+  size_t smem = bytes(threads);
   while (smem > 200 * 1024 && threads > 32) {
     threads >>= 1;
-    smem = (size_t) nacc * sizeof(double) * (threads / 32);
+    smem = bytes(threads);
   }
   if (smem > 200 * 1024) {
     set_error("too many (multipole x k-bin) accumulators for the binning kernel: %d\n", nacc);
@@ -279,7 +283,7 @@ int run_spectrum(const BinGeom &g, const void *Fa0, const void *Fa1, const void 
   auto kern = k_spectrum<real, NV, MODE, IL>;
   const int nacc = NV * g.nbin;
   LaunchShape ls;
-  if (shape_for(kern, nacc, ls)) return -1;
+  if (shape_for(kern, nacc, g.nbin, ls)) return -1;
   const int half = (g.ng >> 1) + 1;
   size_t rows = (size_t) ((MODE == MODE_GEOM && g.symx) ? half : g.nyloc)
       * ((MODE == MODE_GEOM && g.symy) ? half : g.ng);
@@ -481,8 +485,8 @@ __global__ void __launch_bounds__(256) k_ylm_accum_k(YlmGeom g, BinGeom bg, doub
     const double k2 = ki * ki + kj * kj;
     const double k2ij = __dadd_rn(bg.kax2[0][i], bg.kax2[1][j]);
     for (int k = threadIdx.x; k < g.ngk; k += blockDim.x) {
-      double kmod;
-      if (bin_of(bg, __dadd_rn(k2ij, bg.kax2[2][k]), kmod) < 0) continue;
+      const double k2b = __dadd_rn(k2ij, bg.kax2[2][k]);
+      if (!(k2b >= bg.k2edge[0]) || k2b >= bg.k2edge[bg.nbin]) continue;   // unused cell
       const double kk = f2 * k;
       const double k3 = sqrt(k2 + kk * kk);
       double sh = 1.0;

@@ -505,9 +505,10 @@ double window_axis(int intlace, int scheme, double x) {
   }
 }
 
-// the reference's bin decision for log bins, src/multipole.c:145-159, with libm
-int ref_log_bin(double k2, double k0, double k1, double dk, int nbin) {
-  const double kc = 0.5 * log10(k2);
+// the reference's bin decision, src/multipole.c:145-159 (linear: sqrt; log: glibc
+// log10), evaluated on the host with exactly the reference's operations
+int ref_bin(double k2, bool logk, double k0, double k1, double dk, int nbin) {
+  const double kc = logk ? 0.5 * log10(k2) : sqrt(k2);
   if (kc < k0 || kc >= k1) return -1;
   const int b = (int) ((kc - k0) / dk);
   return (b < 0 || b >= nbin) ? -1 : b;
@@ -515,6 +516,7 @@ int ref_log_bin(double k2, double k0, double k1, double dk, int nbin) {
 
 // smallest positive double x with pred(x) true, pred monotone false -> true
 template <typename F> double bisect_first(F pred) {
+  if (pred(0.0)) return 0.0;
   uint64_t lo = 1, hi = 0x7fefffffffffffffull;  // smallest subnormal .. DBL_MAX
   auto val = [](uint64_t u) { double d; memcpy(&d, &u, 8); return d; };
   if (!pred(val(hi))) return INFINITY;
@@ -645,16 +647,19 @@ int prepare_bins(psb_context *c, const psb_params *par) {
       ps[i] = sin(ph);
     }
   }
-  if (par->logscale) {
+  {
+    // smallest k^2 that the reference's arithmetic puts in bin >= b (or past the
+    // last edge): a monotone predicate, bisected over the doubles
+    const bool lg = par->logscale;
     const double k0 = c->kedge[0], k1 = c->kedge[nbin], dk = par->kbin;
     double *e = &T[15 * tlen];
+    auto coord = [lg](double x) { return lg ? 0.5 * log10(x) : sqrt(x); };
     for (int b = 0; b < nbin; b++)
       e[b] = bisect_first([&](double x) {
-        const double kc = 0.5 * log10(x);
-        if (kc >= k1) return true;
-        return ref_log_bin(x, k0, k1, dk, nbin) >= b;
+        if (coord(x) >= k1) return true;
+        return ref_bin(x, lg, k0, k1, dk, nbin) >= b;
       });
-    e[nbin] = bisect_first([&](double x) { return 0.5 * log10(x) >= k1; });
+    e[nbin] = bisect_first([&](double x) { return coord(x) >= k1; });
   }
   if (c->tables.reserve(T.size() * sizeof(double))) return -1;
   BinGeom &bg = c->bg;
@@ -672,8 +677,8 @@ int prepare_bins(psb_context *c, const psb_params *par) {
     bg.wax[a] = base + (6 + a) * tlen;
     bg.pc[a] = base + (9 + a) * tlen; bg.ps[a] = base + (12 + a) * tlen;
   }
-  bg.k2edge = par->logscale ? c->tables.as<double>() + 15 * tlen : nullptr;
-  bg.k0 = c->kedge[0]; bg.k1 = c->kedge[nbin]; bg.dk = par->kbin;
+  bg.k2edge = c->tables.as<double>() + 15 * tlen;
+  bg.k0 = c->kedge[0]; bg.k1 = c->kedge[nbin]; bg.dk = par->kbin; bg.inv_dk = 1.0 / par->kbin;
 
   const size_t nacc = (size_t) nl * nbin;
   const size_t sb = bin_scratch_bytes(bg);

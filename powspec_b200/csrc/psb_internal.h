@@ -68,12 +68,13 @@ struct BinGeom {
   double k0;            // kedge[0]
   double k1;            // kedge[nbin]
   double dk;
+  double inv_dk;
   // device tables, each of length ng (axis 2: ngk entries used)
   const double *kax[3];         // k_a(n)        src/multipole.c:130-141
   const double *kax2[3];        // k_a(n)^2
   const double *wax[3];         // window factor src/multipole.c:46-100
   const double *pc[3], *ps[3];  // cos/sin(pi n / Ng), interlace phase, :462-484
-  const double *k2edge;         // [nbin+1] thresholds in k^2 (log bins) or null
+  const double *k2edge;         // [nbin+1] smallest k^2 landing in each bin (host-bisected)
 };
 
 // geometry-only pass: cnt (u64), km (sum of |k| or log k), lcnt[nl][nbin]
