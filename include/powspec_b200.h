@@ -152,6 +152,35 @@ int psb_set_option(psb_context *ctx, const char *name, long value);
 const char *psb_last_error(void);
 int psb_device_count(void);
 
+/* ---------------------------------------------------------------------------
+ * Slab-decomposed mesh for meshes that exceed or strain one GPU.
+ * The reference has no distributed path (one address space, src/genr_mesh.c:650-747);
+ * this is new design.  Rank r of nranks owns the x-planes [r*Ng/nranks,
+ * (r+1)*Ng/nranks) of every real field.  These entry points are the per-rank
+ * building blocks; the exchanges between them — particle routing (all-to-all-v),
+ * halo planes (neighbour send/recv + psb_add), FFT transpose (all-to-all),
+ * bin sums (allreduce) — are issued by the host over NCCL
+ * (powspec_b200/distributed.py).  All buffers are caller-owned device memory.
+ * Simulation boxes only. */
+typedef struct { int nranks, rank; } psb_slab;
+#define PSB_HALO_LO 1   /* halo planes below the slab (TSC/PCS reach i0-1)               */
+#define PSB_HALO_HI 3   /* above: i0+2, +1 for the half-cell shifted (interlaced) field */
+/* reals in one slab buffer: (nx + halos) * Ng * 2(Ng/2+1); nranks == 1: no halos */
+size_t psb_slab_mesh_elems(const psb_params *par, const psb_slab *slab);
+int psb_slab_partition(psb_context *ctx, const psb_params *par, int nranks,
+    const double *particles_dev, size_t n, double *sorted_dev, size_t *counts);
+int psb_slab_assign(psb_context *ctx, const psb_params *par, const psb_slab *slab,
+    const double *particles_dev, size_t n, double wscale, void *mesh0, void *mesh1);
+int psb_add(psb_context *ctx, void *dst, const void *src, size_t n, int precision);
+int psb_slab_fft_yz(psb_context *ctx, const psb_params *par, const psb_slab *slab, void *owned);
+int psb_slab_pack(psb_context *ctx, const psb_params *par, const psb_slab *slab,
+    const void *owned, void *sendbuf);
+int psb_slab_fft_x(psb_context *ctx, const psb_params *par, const psb_slab *slab, void *buf);
+int psb_slab_bin(psb_context *ctx, const psb_params *par, const psb_slab *slab,
+    const void *Fa0, const void *Fa1, const void *Fb0, const void *Fb1, double *pl_dev);
+psb_result *psb_slab_finish(psb_context *ctx, const psb_params *par, const double *pl0,
+    const double *pl1, const double *xpl, const double wdata[2]);
+
 /* Device-side synthetic catalogue generator for benchmarks:
  * fills n x {x,y,z,w} on the device; kind 0 = uniform in [0,L)^3, 1 = clustered.
  * Returns a device pointer to be released with psb_device_free. */

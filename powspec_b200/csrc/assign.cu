@@ -95,7 +95,10 @@ __global__ void __launch_bounds__(256) k_row_keys(const double2 *__restrict__ p,
     int cy = base_cell(grid_coord(a.y, g.org[1], g.len[1], g.ng), g.ng);
     // strip-major row order: the sweep over x stays inside a strip of
     // g.strip rows, so the planes it touches fit in L2
-    uint32_t key = ((uint32_t) (cy / g.strip) * (uint32_t) g.ng + (uint32_t) cx)
+    int cxl = cx - g.x0;                // plane index inside the owned x-slab
+    if (cxl < 0) cxl += g.ng;
+    if (cxl >= g.nx) cxl = g.nx - 1;    // not ours (caller's routing error): keep the key in range
+    uint32_t key = ((uint32_t) (cy / g.strip) * (uint32_t) g.nx + (uint32_t) cxl)
         * (uint32_t) g.strip + (uint32_t) (cy % g.strip);
     keys[i] = key;
     atomicAdd(hist + key, 1u);
@@ -123,7 +126,7 @@ static int grid_for(size_t n, int per_block, int max_blocks) {
 
 size_t row_key_count(const AssignGeom &g) {
   const size_t nstrip = ((size_t) g.ng + g.strip - 1) / g.strip;
-  return nstrip * (size_t) g.ng * (size_t) g.strip;
+  return nstrip * (size_t) g.nx * (size_t) g.strip;
 }
 
 int launch_row_keys(const double *p, size_t n, const AssignGeom &g, uint32_t *keys,
@@ -192,6 +195,15 @@ __device__ __forceinline__ void axis_stencil(double t, int ng, int (&idx)[SCHEME
   }
 }
 
+// x-plane of the global mesh -> plane of the local buffer (slab decomposition:
+// the buffer holds planes xbase .. xbase+nxloc-1 of the periodic mesh, i.e. the
+// owned slab plus its halo planes; single GPU: xbase = 0, nxloc = Ng)
+__device__ __forceinline__ int local_plane(int ix, const AssignGeom &g) {
+  int lp = ix - g.xbase;
+  if (lp < 0) lp += g.ng;
+  return lp;
+}
+
 template <typename real> __device__ __forceinline__ void red_add(real *addr, double v) {
   atomicAdd(addr, (real) v);    // result unused -> RED.E.ADD.F64 / .F32
 }
@@ -212,10 +224,12 @@ __device__ __forceinline__ void scatter_one(const double x[3], double pw,
   for (int a = 0; a < NS; a++) wx[a] *= pw;
 #pragma unroll
   for (int a = 0; a < NS; a++) {
+    const int lp = local_plane(ix[a], g);
+    if (lp >= g.nxloc) continue;        // outside this slab's buffer (never for routed particles)
 #pragma unroll
     for (int b = 0; b < NS; b++) {
       const double wxy = wx[a] * wy[b];
-      real *row = mesh + ((size_t) ix[a] * g.ng + iy[b]) * g.rowlen;
+      real *row = mesh + ((size_t) lp * g.ng + iy[b]) * g.rowlen;
 #pragma unroll
       for (int c = 0; c < NS; c++) red_add(row + iz[c], wxy * wz[c]);
     }
@@ -351,9 +365,11 @@ __device__ __forceinline__ void scatter_coop(const double x[3], double pw, const
   for (int a = 0; a < NS; a++) wx[a] *= pw;
 #pragma unroll
   for (int a = 0; a < NS; a++) {
+    const int lp = local_plane(ix[a], g);
+    if (lp >= g.nxloc) continue;        // outside this slab's buffer (never for routed particles)
 #pragma unroll
     for (int b = 0; b < NS; b++) {
-      real *row = mesh + ((size_t) ix[a] * g.ng + iy[b]) * g.rowlen;
+      real *row = mesh + ((size_t) lp * g.ng + iy[b]) * g.rowlen;
       red_add(row + izc, (wx[a] * wy[b]) * wzc);
     }
   }
@@ -444,6 +460,54 @@ int launch_assign(const double *p, size_t n, const AssignGeom &g, int scheme,
       return -1;
   }
 #undef PSB_DISPATCH
+}
+
+// ---------------------------------------------------------------------------
+// slab decomposition helpers: owner of a particle = slab of its base x-cell
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_owner_keys(const double2 *__restrict__ p, size_t n,
+    AssignGeom g, int nranks, uint32_t *__restrict__ keys, uint32_t *__restrict__ hist) {
+  __shared__ uint32_t sh[64];
+  if (threadIdx.x < 64) sh[threadIdx.x] = 0;
+  __syncthreads();
+  const int per = g.ng / nranks;
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n;
+       i += (size_t) gridDim.x * blockDim.x) {
+    double2 a = __ldg(p + 2 * i);
+    int cx = base_cell(grid_coord(a.x, g.org[0], g.len[0], g.ng), g.ng);
+    int r = cx / per;
+    if (r >= nranks) r = nranks - 1;
+    keys[i] = (uint32_t) r;
+    atomicAdd(&sh[r], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < nranks && sh[threadIdx.x]) atomicAdd(hist + threadIdx.x, sh[threadIdx.x]);
+}
+
+int launch_owner_keys(const double *p, size_t n, const AssignGeom &g, int nranks, uint32_t *keys,
+    uint32_t *hist, cudaStream_t st) {
+  if (nranks > 64) { set_error("at most 64 slabs are supported\n"); return -1; }
+  k_owner_keys<<<grid_for(n, 256, 148 * 16), 256, 0, st>>>(
+      reinterpret_cast<const double2 *>(p), n, g, nranks, keys, hist);
+  PSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename real>
+__global__ void k_add(real *__restrict__ dst, const real *__restrict__ src, size_t n) {
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n;
+       i += (size_t) gridDim.x * blockDim.x)
+    dst[i] += src[i];
+}
+
+int launch_add(void *dst, const void *src, size_t n, int precision, cudaStream_t st) {
+  if (!n) return 0;
+  if (precision == 8)
+    k_add<double><<<grid_for(n, 256, 148 * 16), 256, 0, st>>>((double *) dst, (const double *) src, n);
+  else
+    k_add<float><<<grid_for(n, 256, 148 * 16), 256, 0, st>>>((float *) dst, (const float *) src, n);
+  PSB_CUDA(cudaGetLastError());
+  return 0;
 }
 
 // ---------------------------------------------------------------------------

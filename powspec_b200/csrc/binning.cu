@@ -122,12 +122,12 @@ __global__ void __launch_bounds__(256) k_spectrum(BinGeom g, const void *__restr
   // (y) component the summands are even in n_x (n_y) — k^2 tables are exactly
   // symmetric — so only n >= 0 is visited and doubled (exact in binary FP).
   const int half = (g.ng >> 1) + 1;
-  const int nI = (MODE == MODE_GEOM && g.symx) ? half : g.nyloc;
-  const int nJ = (MODE == MODE_GEOM && g.symy) ? half : g.ng;
+  const int nI = (MODE == MODE_GEOM && g.symx) ? half : g.ng;
+  const int nJ = (MODE == MODE_GEOM && g.symy) ? half : g.nj;
   const size_t nrows = (size_t) nI * nJ;
   const size_t wstride = (size_t) gridDim.x * nwarp;
   for (size_t row = (size_t) blockIdx.x * nwarp + warp; row < nrows; row += wstride) {
-    const int i = g.y0 + (int) (row / nJ), j = (int) (row % nJ);
+    const int i = (int) (row / nJ), j = g.j0 + (int) (row % nJ);
     double wsym = 1.0;
     if (MODE == MODE_GEOM) {
       const bool self_i = (i == 0) || (((g.ng & 1) == 0) && i == (g.ng >> 1));
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256) k_spectrum(BinGeom g, const void *__restr
       pcij = ci * cj - si * sj;
       psij = si * cj + ci * sj;
     }
-    const size_t rbase = ((size_t) (i - g.y0) * g.ng + j) * (size_t) g.ngk;
+    const size_t rbase = ((size_t) i * g.nj + (j - g.j0)) * (size_t) g.ngk;
     for (int kb = 0; kb < g.ngk; kb += 32) {
       const int k = kb + lane;
       int key = -1;
@@ -285,8 +285,8 @@ int run_spectrum(const BinGeom &g, const void *Fa0, const void *Fa1, const void 
   LaunchShape ls;
   if (shape_for(kern, nacc, g.nbin, ls)) return -1;
   const int half = (g.ng >> 1) + 1;
-  size_t rows = (size_t) ((MODE == MODE_GEOM && g.symx) ? half : g.nyloc)
-      * ((MODE == MODE_GEOM && g.symy) ? half : g.ng);
+  size_t rows = (size_t) ((MODE == MODE_GEOM && g.symx) ? half : g.ng)
+      * ((MODE == MODE_GEOM && g.symy) ? half : g.nj);
   size_t need_blocks = (rows + ls.threads / 32 - 1) / (ls.threads / 32);
   if ((size_t) ls.blocks > need_blocks) ls.blocks = (int) need_blocks;
   if (ls.blocks > MAX_BLOCKS) ls.blocks = MAX_BLOCKS;
@@ -368,9 +368,9 @@ template <typename real>
 __global__ void __launch_bounds__(256) k_combine(BinGeom g, typename C2<real>::type *F0,
     const typename C2<real>::type *__restrict__ F1) {
   using c2 = typename C2<real>::type;
-  const size_t nrows = (size_t) g.nyloc * g.ng;
+  const size_t nrows = (size_t) g.ng * g.nj;
   for (size_t row = blockIdx.x; row < nrows; row += gridDim.x) {
-    const int i = g.y0 + (int) (row / g.ng), j = (int) (row % g.ng);
+    const int i = (int) (row / g.nj), j = g.j0 + (int) (row % g.nj);
     const double ci = g.pc[0][i], si = g.ps[0][i], cj = g.pc[1][j], sj = g.ps[1][j];
     const double cij = ci * cj - si * sj, sij = si * cj + ci * sj;
     for (int k = threadIdx.x; k < g.ngk; k += blockDim.x) {

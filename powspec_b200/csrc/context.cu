@@ -127,6 +127,11 @@ struct psb_context {
   bool have_fwd = false, have_inv = false;
   DevBuf fftwork;
 
+  // slab-decomposed FFT plans
+  cufftHandle slab_yz = 0, slab_x = 0;
+  int slab_ng = 0, slab_nx = 0, slab_prec = 0;
+  bool slab_have = false;
+
   // tables and bins
   DevBuf tables, binscratch, bins;
   std::vector<double> host_tables;
@@ -585,6 +590,66 @@ int fft_inverse(psb_context *c, void *mesh) {
 }
 
 
+// count_mode's normalisation and shot-noise subtraction (src/multipole.c:1047-1161)
+// and the log-bin rescaling of powspec() (:1267-1274, quirk Q7); O(nl * nbin) on the host
+void normalise(psb_result *res, const psb_params *par, bool issim, int nc, const double *shot,
+    const double *norm) {
+  const int nl = res->nl, nbin = res->nbin;
+  if (issim) {
+    for (int i = 0; i < nc; i++) {
+      if (!res->has_pl[i]) continue;
+      for (int l = 0; l < nl; l++)
+        for (int b = 0; b < nbin; b++) {
+          double &p = res->pl[i][(size_t) l * nbin + b];
+          if (res->cnt[b]) {
+            p /= norm[i] * res->cnt[b];
+            p -= shot[i] * res->lcnt[(size_t) l * nbin + b] / res->cnt[b];
+          }
+          p *= 2 * par->poles[l] + 1;
+        }
+    }
+    if (res->has_xpl)
+      for (int l = 0; l < nl; l++)
+        for (int b = 0; b < nbin; b++) {
+          double &p = res->xpl[(size_t) l * nbin + b];
+          if (res->cnt[b]) p /= sqrt(norm[0] * norm[1]) * res->cnt[b];
+          p *= 2 * par->poles[l] + 1;
+        }
+  }
+  else {
+    for (int i = 0; i < nc; i++) {
+      if (!res->has_pl[i]) continue;
+      if (par->poles[0] == 0)
+        for (int b = 0; b < nbin; b++)
+          if (res->cnt[b]) {
+            double &p = res->pl[i][b];
+            p = p / res->cnt[b] - shot[i];
+            p /= norm[i];
+          }
+      for (int n = 1; n < nl; n++)
+        for (int b = 0; b < nbin; b++)
+          if (res->cnt[b]) res->pl[i][(size_t) n * nbin + b] *= 4 * PI / (norm[i] * res->cnt[b]);
+    }
+    if (res->has_xpl) {
+      if (par->poles[0] == 0)
+        for (int b = 0; b < nbin; b++)
+          if (res->cnt[b]) res->xpl[b] /= sqrt(norm[0] * norm[1]) * res->cnt[b];
+      for (int n = 1; n < nl; n++)
+        for (int b = 0; b < nbin; b++)
+          if (res->cnt[b])
+            res->xpl[(size_t) n * nbin + b] *= 2 * PI / (sqrt(norm[0] * norm[1]) * res->cnt[b]);
+    }
+  }
+  if (par->logscale) {          // quirk Q7, src/multipole.c:1267-1274
+    for (int i = 0; i < nbin; i++) {
+      res->k[i] = pow(10, res->k[i]);
+      res->km[i] = pow(10, res->k[i]);
+      res->kedge[i] = pow(10, res->k[i]);
+    }
+    res->kedge[nbin] = pow(10, res->kedge[nbin]);
+  }
+}
+
 // powspec_init (src/multipole.c:335-394) + the per-axis tables + powspec_precomp
 // (src/multipole.c:111-257).  Everything here is independent of the particles,
 // so psb_mesh launches it on the side stream before the scatter: the
@@ -667,7 +732,7 @@ int prepare_bins(psb_context *c, const psb_params *par) {
   bg.ng = ng; bg.ngk = ngk; bg.nbin = nbin; bg.nl = nl;
   for (int i = 0; i < nl; i++) bg.poles[i] = par->poles[i];
   bg.issim = issim; bg.logk = par->logscale; bg.intlace = il;
-  bg.y0 = 0; bg.nyloc = ng;
+  bg.j0 = 0; bg.nj = ng;
   bg.symx = c->opt_geom_sym && (!issim || par->los[0] == 0.0);
   bg.symy = c->opt_geom_sym && (!issim || par->los[1] == 0.0);
   for (int a = 0; a < 3; a++) {
@@ -749,6 +814,7 @@ void psb_destroy(psb_context *c) {
   cudaDeviceSynchronize();
   if (c->have_fwd) cufftDestroy(c->plan_fwd);
   if (c->have_inv) cufftDestroy(c->plan_inv);
+  if (c->slab_have) { cufftDestroy(c->slab_yz); cufftDestroy(c->slab_x); }
   for (int i = 0; i < 2; i++) {
     for (int j = 0; j < 2; j++) { c->part_in[i][j].release(); c->mesh[i][j].release(); }
     c->fkl[i].release(); c->fk0copy[i].release();
@@ -842,6 +908,7 @@ int psb_mesh(psb_context *c, const psb_params *par, const psb_cats *cats) {
   g.ng = ng; g.rowlen = rowlen;
   g.strip = (int) std::min<long>(std::max<long>(c->opt_strip, 1), ng);
   g.coop = (int) c->opt_coop;
+  g.x0 = 0; g.nx = ng; g.xbase = 0; g.nxloc = ng;
   for (int a = 0; a < 3; a++) {
     g.org[a] = c->bmin[a];
     g.len[a] = c->bsize[a];
@@ -1104,61 +1171,8 @@ psb_result *psb_power(psb_context *c, const psb_params *par) {
         hb.begin() + 2 * nbin + (2 + i) * nacc);
   if (res->has_xpl) res->xpl.assign(hb.begin() + 2 * nbin + 3 * nacc, hb.begin() + 2 * nbin + 4 * nacc);
 
-  // ---- count_mode normalisation, src/multipole.c:1047-1161
   const double *shot = c->shot, *norm = c->norm;
-  if (issim) {
-    for (int i = 0; i < nc; i++) {
-      if (!res->has_pl[i]) continue;
-      for (int l = 0; l < nl; l++)
-        for (int b = 0; b < nbin; b++) {
-          double &p = res->pl[i][(size_t) l * nbin + b];
-          if (res->cnt[b]) {
-            p /= norm[i] * res->cnt[b];
-            p -= shot[i] * res->lcnt[(size_t) l * nbin + b] / res->cnt[b];
-          }
-          p *= 2 * par->poles[l] + 1;
-        }
-    }
-    if (res->has_xpl)
-      for (int l = 0; l < nl; l++)
-        for (int b = 0; b < nbin; b++) {
-          double &p = res->xpl[(size_t) l * nbin + b];
-          if (res->cnt[b]) p /= sqrt(norm[0] * norm[1]) * res->cnt[b];
-          p *= 2 * par->poles[l] + 1;
-        }
-  }
-  else {
-    for (int i = 0; i < nc; i++) {
-      if (!res->has_pl[i]) continue;
-      if (par->poles[0] == 0)
-        for (int b = 0; b < nbin; b++)
-          if (res->cnt[b]) {
-            double &p = res->pl[i][b];
-            p = p / res->cnt[b] - shot[i];
-            p /= norm[i];
-          }
-      for (int n = 1; n < nl; n++)
-        for (int b = 0; b < nbin; b++)
-          if (res->cnt[b]) res->pl[i][(size_t) n * nbin + b] *= 4 * PI / (norm[i] * res->cnt[b]);
-    }
-    if (res->has_xpl) {
-      if (par->poles[0] == 0)
-        for (int b = 0; b < nbin; b++)
-          if (res->cnt[b]) res->xpl[b] /= sqrt(norm[0] * norm[1]) * res->cnt[b];
-      for (int n = 1; n < nl; n++)
-        for (int b = 0; b < nbin; b++)
-          if (res->cnt[b])
-            res->xpl[(size_t) n * nbin + b] *= 2 * PI / (sqrt(norm[0] * norm[1]) * res->cnt[b]);
-    }
-  }
-  if (par->logscale) {          // quirk Q7, src/multipole.c:1267-1274
-    for (int i = 0; i < nbin; i++) {
-      res->k[i] = pow(10, res->k[i]);
-      res->km[i] = pow(10, res->k[i]);
-      res->kedge[i] = pow(10, res->k[i]);
-    }
-    res->kedge[nbin] = pow(10, res->kedge[nbin]);
-  }
+  normalise(res, par, issim, nc, shot, norm);
   for (int i = 0; i < 2; i++) { res->shot[i] = i < nc ? shot[i] : 0; res->norm[i] = i < nc ? norm[i] : 0; }
   for (int a = 0; a < 3; a++) { res->bmin[a] = c->bmin[a]; res->bsize[a] = c->bsize[a]; res->bmax[a] = c->bmax[a]; }
   c->mesh_ready = false;        // the FFTs ran in place: the meshes are consumed
@@ -1208,6 +1222,236 @@ int psb_timings(const psb_context *c, double *ms, int n) {
 }
 
 long psb_launch_count(const psb_context *c) { return c ? c->launches : -1; }
+
+
+// ---------------------------------------------------------------------------
+// Slab-decomposed mesh: building blocks for one rank.  The
+// collectives between them (particle routing, halo planes, FFT transpose,
+// allreduce of the bins) are issued by the host over NCCL
+// (powspec_b200/distributed.py); buffers are caller-owned device memory.
+// Simulation boxes only (BASELINE configs 4 and 5).
+// ---------------------------------------------------------------------------
+static int slab_geom(psb_context *c, const psb_params *par, const psb_slab *sl, AssignGeom &g) {
+  if (check_params(par)) return -1;
+  if (!par->issim) { set_error("the slab-decomposed path handles simulation boxes only\n"); return -1; }
+  if (!sl || sl->nranks < 1 || sl->rank < 0 || sl->rank >= sl->nranks ||
+      par->gsize % sl->nranks || (sl->nranks > 1 && par->gsize / sl->nranks < PSB_HALO_HI)) {
+    set_error("invalid slab decomposition: GRID_SIZE %d over %d ranks\n", par->gsize,
+        sl ? sl->nranks : 0);
+    return -1;
+  }
+  const int ng = par->gsize, nx = ng / sl->nranks;
+  memset(&g, 0, sizeof g);
+  g.ng = ng; g.rowlen = 2 * (ng / 2 + 1);
+  g.strip = (int) std::min<long>(std::max<long>(c->opt_strip, 1), ng);
+  g.coop = (int) c->opt_coop;
+  g.x0 = sl->rank * nx; g.nx = nx;
+  if (sl->nranks == 1) { g.xbase = 0; g.nxloc = ng; }
+  else { g.xbase = (g.x0 - PSB_HALO_LO + ng) % ng; g.nxloc = nx + PSB_HALO_LO + PSB_HALO_HI; }
+  for (int a = 0; a < 3; a++) {
+    c->bmin[a] = 0; c->bsize[a] = par->bsize[a];
+    g.org[a] = 0; g.len[a] = par->bsize[a]; g.inv_len[a] = 1.0 / par->bsize[a];
+    g.sorg[a] = -0.5 * par->bsize[a] / ng;
+  }
+  return 0;
+}
+
+size_t psb_slab_mesh_elems(const psb_params *par, const psb_slab *sl) {
+  if (!par || !sl || sl->nranks < 1 || par->gsize % sl->nranks) return 0;
+  const size_t ng = par->gsize, nx = ng / sl->nranks;
+  const size_t planes = sl->nranks == 1 ? ng : nx + PSB_HALO_LO + PSB_HALO_HI;
+  return planes * ng * 2 * (ng / 2 + 1);
+}
+
+// group the particles by owning slab (owner = slab of the base x-cell on the
+// unshifted grid); counts[r] particles for rank r, contiguous in `sorted`
+int psb_slab_partition(psb_context *c, const psb_params *par, int nranks, const double *particles,
+    size_t n, double *sorted, size_t *counts) {
+  if (!c) { set_error("no device context\n"); return -1; }
+  psb_slab sl = {nranks, 0};
+  AssignGeom g;
+  if (slab_geom(c, par, &sl, g)) return -1;
+  PSB_CUDA(cudaSetDevice(c->device));
+  for (int r = 0; r < nranks; r++) counts[r] = 0;
+  if (!n) return 0;
+  if (n > 0xffffffffull) { set_error("too many particles in one partition call\n"); return -1; }
+  if (c->keys.reserve(n * 4) || c->hist.reserve(64 * 4) || c->cursor.reserve(64 * 4)) return -1;
+  PSB_CUDA(cudaMemsetAsync(c->hist.p, 0, 64 * 4, c->st));
+  if (launch_owner_keys(particles, n, g, nranks, c->keys.as<uint32_t>(), c->hist.as<uint32_t>(), c->st))
+    return -1;
+  uint32_t h[64];
+  PSB_CUDA(cudaMemcpyAsync(h, c->hist.p, 64 * 4, cudaMemcpyDeviceToHost, c->st));
+  PSB_CUDA(cudaStreamSynchronize(c->st));
+  uint32_t cur[64], acc = 0;
+  for (int r = 0; r < 64; r++) { cur[r] = acc; if (r < nranks) { counts[r] = h[r]; acc += h[r]; } }
+  PSB_CUDA(cudaMemcpyAsync(c->cursor.p, cur, 64 * 4, cudaMemcpyHostToDevice, c->st));
+  if (launch_row_scatter(particles, n, c->keys.as<uint32_t>(), c->cursor.as<uint32_t>(), sorted, c->st))
+    return -1;
+  PSB_CUDA(cudaStreamSynchronize(c->st));
+  c->launches += 2;
+  return 0;
+}
+
+// scatter the rank's particles into its slab buffers (owned planes + halos);
+// the buffers must have been zeroed by the caller; mesh1 NULL without interlacing
+int psb_slab_assign(psb_context *c, const psb_params *par, const psb_slab *sl,
+    const double *particles, size_t n, double wscale, void *mesh0, void *mesh1) {
+  if (!c) { set_error("no device context\n"); return -1; }
+  AssignGeom g;
+  if (slab_geom(c, par, sl, g)) return -1;
+  PSB_CUDA(cudaSetDevice(c->device));
+  if (par->intlace && !mesh1) { set_error("interlacing needs the second mesh\n"); return -1; }
+  if (assign_catalog(c, particles, n, g, par->assign, par->precision, wscale, mesh0,
+        par->intlace ? mesh1 : nullptr))
+    return -1;
+  PSB_CUDA(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+int psb_add(psb_context *c, void *dst, const void *src, size_t n, int precision) {
+  if (!c) return -1;
+  PSB_CUDA(cudaSetDevice(c->device));
+  if (launch_add(dst, src, n, precision, c->st)) return -1;
+  PSB_CUDA(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+static int slab_plans(psb_context *c, int ng, int nx, int prec) {
+  if (c->slab_ng == ng && c->slab_nx == nx && c->slab_prec == prec) return 0;
+  if (c->slab_have) { cufftDestroy(c->slab_yz); cufftDestroy(c->slab_x); c->slab_have = false; }
+  const int ngk = ng / 2 + 1;
+  long long n2[2] = {ng, ng}, rembed[2] = {ng, 2LL * ngk}, cembed[2] = {ng, ngk};
+  size_t ws = 0;
+  PSB_CUFFT(cufftCreate(&c->slab_yz));
+  PSB_CUFFT(cufftMakePlanMany64(c->slab_yz, 2, n2, rembed, 1, (long long) ng * 2 * ngk, cembed, 1,
+      (long long) ng * ngk, prec == 8 ? CUFFT_D2Z : CUFFT_R2C, nx, &ws));
+  PSB_CUFFT(cufftSetStream(c->slab_yz, c->st));
+  // after the transpose a rank holds (Ng_x, ny, Ngk): x has stride ny*Ngk
+  long long n1[1] = {ng}, embed[1] = {ng};
+  const long long lines = (long long) nx * ngk;       // ny == nx
+  PSB_CUFFT(cufftCreate(&c->slab_x));
+  PSB_CUFFT(cufftMakePlanMany64(c->slab_x, 1, n1, embed, lines, 1, embed, lines, 1,
+      prec == 8 ? CUFFT_Z2Z : CUFFT_C2C, lines, &ws));
+  PSB_CUFFT(cufftSetStream(c->slab_x, c->st));
+  c->slab_ng = ng; c->slab_nx = nx; c->slab_prec = prec; c->slab_have = true;
+  return 0;
+}
+
+// 2-D r2c over (y, z) of every owned x-plane, in place; `owned` points at the
+// first owned plane of the slab buffer
+int psb_slab_fft_yz(psb_context *c, const psb_params *par, const psb_slab *sl, void *owned) {
+  if (!c) return -1;
+  AssignGeom g;
+  if (slab_geom(c, par, sl, g)) return -1;
+  PSB_CUDA(cudaSetDevice(c->device));
+  if (slab_plans(c, g.ng, g.nx, par->precision)) return -1;
+  if (par->precision == 8)
+    PSB_CUFFT(cufftExecD2Z(c->slab_yz, (cufftDoubleReal *) owned, (cufftDoubleComplex *) owned));
+  else
+    PSB_CUFFT(cufftExecR2C(c->slab_yz, (cufftReal *) owned, (cufftComplex *) owned));
+  PSB_CUDA(cudaStreamSynchronize(c->st));
+  c->launches++;
+  return 0;
+}
+
+// pack the owned planes (nx, Ng, Ngk) complex into the all-to-all send layout
+// [dest rank q][x local][y in slab q][k]
+int psb_slab_pack(psb_context *c, const psb_params *par, const psb_slab *sl, const void *owned,
+    void *sendbuf) {
+  if (!c) return -1;
+  AssignGeom g;
+  if (slab_geom(c, par, sl, g)) return -1;
+  PSB_CUDA(cudaSetDevice(c->device));
+  const size_t csz = 2 * (size_t) par->precision, ngk = g.ng / 2 + 1, ny = g.nx;
+  const size_t width = ny * ngk * csz, spitch = (size_t) g.ng * ngk * csz;
+  for (int q = 0; q < sl->nranks; q++)
+    PSB_CUDA(cudaMemcpy2DAsync(static_cast<char *>(sendbuf) + (size_t) q * g.nx * width, width,
+        static_cast<const char *>(owned) + (size_t) q * width, spitch, width, g.nx,
+        cudaMemcpyDeviceToDevice, c->st));
+  PSB_CUDA(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+// 1-D c2c along x of the received (Ng_x, ny, Ngk) block, in place
+int psb_slab_fft_x(psb_context *c, const psb_params *par, const psb_slab *sl, void *buf) {
+  if (!c) return -1;
+  AssignGeom g;
+  if (slab_geom(c, par, sl, g)) return -1;
+  PSB_CUDA(cudaSetDevice(c->device));
+  if (slab_plans(c, g.ng, g.nx, par->precision)) return -1;
+  if (par->precision == 8)
+    PSB_CUFFT(cufftExecZ2Z(c->slab_x, (cufftDoubleComplex *) buf, (cufftDoubleComplex *) buf, CUFFT_FORWARD));
+  else
+    PSB_CUFFT(cufftExecC2C(c->slab_x, (cufftComplex *) buf, (cufftComplex *) buf, CUFFT_FORWARD));
+  PSB_CUDA(cudaStreamSynchronize(c->st));
+  c->launches++;
+  return 0;
+}
+
+// raw multipole sums of the rank's y-slab, accumulated into pl_dev[nl*nbin]
+// (device memory, so that the host can allreduce it); F*1 NULL without interlacing
+int psb_slab_bin(psb_context *c, const psb_params *par, const psb_slab *sl, const void *Fa0,
+    const void *Fa1, const void *Fb0, const void *Fb1, double *pl_dev) {
+  if (!c) return -1;
+  AssignGeom g;
+  if (slab_geom(c, par, sl, g)) return -1;
+  PSB_CUDA(cudaSetDevice(c->device));
+  if (!same_bins(c, par) && prepare_bins(c, par)) return -1;
+  BinGeom bg = c->bg;
+  bg.j0 = g.x0; bg.nj = g.nx;         // y-slab after the transpose: same split as x
+  PSB_CUDA(cudaStreamWaitEvent(c->st, c->ev_geom, 0));
+  double *scratch_bin = reinterpret_cast<double *>(c->binscratch.as<char>() + c->bin_sb);
+  if (launch_bin(bg, par->precision, Fa0, par->intlace ? Fa1 : nullptr, Fb0,
+        par->intlace ? Fb1 : nullptr, pl_dev, scratch_bin, c->bin_sb, c->st))
+    return -1;
+  PSB_CUDA(cudaStreamSynchronize(c->st));
+  c->launches += 2;
+  return 0;
+}
+
+// mode counts (identical on every rank: pure geometry) + normalisation of the
+// allreduced sums; pl0/pl1/xpl: host arrays of nl*nbin raw sums or NULL
+psb_result *psb_slab_finish(psb_context *c, const psb_params *par, const double *pl0,
+    const double *pl1, const double *xpl, const double wdata[2]) {
+  if (!c) { set_error("no device context\n"); return nullptr; }
+  psb_slab sl = {1, 0};
+  AssignGeom g;
+  if (slab_geom(c, par, &sl, g)) return nullptr;
+  if (cudaSetDevice(c->device) != cudaSuccess) return nullptr;
+  if (!same_bins(c, par) && prepare_bins(c, par)) return nullptr;
+  const int nbin = c->nbin, nl = par->npole, nc = par->ncat;
+  const size_t nacc = (size_t) nl * nbin;
+  psb_result *res = new psb_result();
+  res->nbin = nbin; res->nl = nl;
+  res->kedge = c->kedge; res->k.resize(nbin); res->km.assign(nbin, 0);
+  res->cnt.assign(nbin, 0); res->lcnt.assign(nacc, 0);
+  for (int i = 0; i < nbin; i++) res->k[i] = (res->kedge[i] + res->kedge[i + 1]) * 0.5;
+  std::vector<double> hb(2 * (size_t) nbin + nacc);
+  if (cudaStreamWaitEvent(c->st, c->ev_geom, 0) != cudaSuccess ||
+      cudaMemcpyAsync(hb.data(), c->bins.p, hb.size() * sizeof(double), cudaMemcpyDeviceToHost,
+        c->st) != cudaSuccess || cudaStreamSynchronize(c->st) != cudaSuccess) {
+    set_error("failed to read the mode counts back\n");
+    delete res;
+    return nullptr;
+  }
+  memcpy(res->cnt.data(), hb.data(), nbin * sizeof(double));
+  memcpy(res->km.data(), hb.data() + nbin, nbin * sizeof(double));
+  memcpy(res->lcnt.data(), hb.data() + 2 * nbin, nacc * sizeof(double));
+  for (int b = 0; b < nbin; b++) if (res->cnt[b]) res->km[b] /= res->cnt[b];
+  const double *src[2] = {pl0, pl1};
+  for (int i = 0; i < 2; i++)
+    if (src[i]) { res->has_pl[i] = true; res->pl[i].assign(src[i], src[i] + nacc); }
+  if (xpl) { res->has_xpl = true; res->xpl.assign(xpl, xpl + nacc); }
+  double shot[2] = {0, 0}, norm[2] = {0, 0};
+  const double vol = c->bsize[0] * c->bsize[1] * c->bsize[2];
+  for (int i = 0; i < nc; i++) { shot[i] = vol / wdata[i]; norm[i] = wdata[i] * wdata[i] / vol; }
+  normalise(res, par, true, nc, shot, norm);
+  for (int i = 0; i < 2; i++) { res->shot[i] = shot[i]; res->norm[i] = norm[i]; }
+  for (int a = 0; a < 3; a++) { res->bmin[a] = 0; res->bsize[a] = c->bsize[a]; res->bmax[a] = c->bsize[a]; }
+  c->bins_ready = false;
+  collect_timings(c);
+  return res;
+}
 
 double *psb_generate_catalog(psb_context *c, size_t n, double boxsize, int kind, uint64_t seed) {
   if (!c) { set_error("no device context\n"); return nullptr; }

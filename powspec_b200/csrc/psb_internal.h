@@ -33,6 +33,8 @@ struct AssignGeom {
   int rowlen;           // reals per z-row of the (padded, in-place FFT) mesh
   int strip;            // rows per strip of the sort order (row-key layout)
   int coop;             // z-coalesced scatter (NZ lanes per particle)
+  int x0, nx;           // owned x-planes [x0, x0+nx) (single GPU: 0, Ng)
+  int xbase, nxloc;     // planes held by the local buffer: xbase .. xbase+nxloc-1 (mod Ng)
   double org[3];        // lower box corner (MESH.min)
   double sorg[3];       // corner of the half-cell shifted box (MESH.smin)
   double len[3];        // box size
@@ -53,6 +55,9 @@ int launch_assign(const double *p, size_t n, const AssignGeom &g, int scheme,
     int precision, double wscale, void *mesh0, void *mesh1, cudaStream_t st);
 int launch_unpad_copy(const void *mesh, void *dst, int ng, int rowlen,
     int precision, cudaStream_t st);
+int launch_owner_keys(const double *p, size_t n, const AssignGeom &g, int nranks,
+    uint32_t *keys, uint32_t *hist, cudaStream_t st);
+int launch_add(void *dst, const void *src, size_t n, int precision, cudaStream_t st);
 
 // ---------------------------------------------------------------------------
 // Fourier-space binning (binning.cu)
@@ -62,7 +67,8 @@ struct BinGeom {
   int nbin, nl;
   int poles[8];
   int issim, logk, intlace;
-  int y0, nyloc;        // local range of the slowest index of the k-space array
+  int j0, nj;           // local range of the middle (y) index of the k-space array:
+                        // element (i, j0+jl, k) lives at ((i*nj + jl)*ngk + k)
   int symx, symy;       // mode counting may fold n_x / n_y (los component is zero)
   double los[3];
   double k0;            // kedge[0]
