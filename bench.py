@@ -155,6 +155,58 @@ def run_reference(workload, steps, warmup):
                 t_powspec_s=float(np.mean(tp)), npart=s["npart"], ng=s["ng"])
 
 
+def bench_slab(args, ctx, conf, w, world, rank, local_rank, config, barrier):
+    """ONE mesh over all ranks: total problem fixed (strong scaling)."""
+    import torch
+    import torch.distributed as dist
+
+    from powspec_b200.distributed import GpuSlabEngine, TorchComm, slab_power
+
+    class NoComm:
+        size, rank = 1, 0
+    comm = TorchComm() if world > 1 else NoComm()
+    eng = GpuSlabEngine(ctx, conf, world, rank)
+    n_total = w["npart"]
+    n_loc = n_total // world
+    ptr, _ = ctx.generate_catalog(n_loc, w["box"], kind=args.kind, seed=1 + rank)
+    share = torch.empty((n_loc, 4), dtype=torch.float64, device="cuda")
+    import ctypes
+    ctypes.CDLL("libcudart.so").cudaMemcpy(ctypes.c_void_p(share.data_ptr()), ctypes.c_void_p(ptr),
+                                           ctypes.c_size_t(n_loc * 32), 3)
+    ctx.free_catalog((ptr, n_loc))
+
+    def step():
+        return slab_power(eng, comm, [share], [float(n_loc * world)])
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        pk = step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item()) / args.steps
+    if rank == 0:
+        config = dict(config)
+        config["parallelism"] = f"one {w['ng']}^3 mesh x-slab-decomposed over {world} GPU(s)"
+        config["npart_total"] = n_loc * world
+        print(json.dumps({"metric": "particles_per_second_P_ell_1024_TSC_interlaced",
+                          "value": n_loc * world / (ms_step * 1e-3), "unit": "particles/s",
+                          "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                          "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f64" if args.precision == 8 else "f32",
+                          "data": "synthetic", "config": config, "mode": "slab",
+                          "P0_first_bins": [float(x) for x in pk.pl[0][0][:3]]}))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -169,6 +221,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--opt", action="append", default=[], help="context option name=value (ablations)")
+    ap.add_argument("--mode", default="replica", choices=["replica", "slab"],
+                    help="N>1: 'replica' = one independent catalogue per GPU (weak scaling, default); "
+                         "'slab' = ONE mesh x-slab-decomposed over the GPUs (strong scaling, NCCL "
+                         "all-to-all transpose + halo exchange + allreduce)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -241,6 +297,9 @@ def main():
     def step(cata):
         mesh = ctx.genr_mesh(conf, cata)
         return ctx.powspec(conf, cata, mesh)
+
+    if args.mode == "slab":
+        return bench_slab(args, ctx, conf, w, world, rank, local_rank, config, barrier)
 
     def timed(cata, steps, warmup):
         for _ in range(warmup):

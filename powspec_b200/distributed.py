@@ -194,9 +194,17 @@ class GpuSlabEngine:
             from .api import _err
             raise _err(self.L, what)
 
+    def _enter(self):
+        # torch (allocation memsets, copies, NCCL) works on its own streams and
+        # the library on the context's stream; every psb_slab_* call drains its
+        # stream before returning, so one device synchronisation on entry makes
+        # the hand-over safe in both directions
+        self.torch.cuda.synchronize(self.device)
+
     # route
     def partition(self, particles):
         t = self.torch
+        self._enter()
         n = particles.shape[0]
         out = t.empty_like(particles)
         counts = (C.c_size_t * self.shape.nranks)()
@@ -208,6 +216,7 @@ class GpuSlabEngine:
     # assign: returns the slab buffers [field] as (planes, ng, rowlen) tensors
     def assign(self, particles_flat):
         t, s = self.torch, self.shape
+        self._enter()
         n = particles_flat.numel() // 4
         nf = 2 if self.conf.intlace else 1
         meshes = [t.zeros((s.planes, s.ng, s.rowlen), dtype=self.rdtype, device=self.device)
@@ -219,12 +228,14 @@ class GpuSlabEngine:
         return meshes
 
     def add_into(self, dst, src):
+        self._enter()
         self._chk(self.L.psb_add(self.ctx.h, dst.data_ptr(), src.data_ptr(), src.numel(),
                                  self.conf.precision), "psb_add")
 
     # 2-D FFT on owned planes + pack for the transpose; returns the send buffer
     def fft_yz_pack(self, mesh):
         t, s = self.torch, self.shape
+        self._enter()
         owned = mesh[s.lo:s.lo + s.nx]
         self._chk(self.L.psb_slab_fft_yz(self.ctx.h, C.byref(self.par), C.byref(self.slab),
                                          owned.data_ptr()), "psb_slab_fft_yz")
@@ -238,6 +249,7 @@ class GpuSlabEngine:
         return self.torch.empty(s.nx * s.ng * s.ngk * 2, dtype=self.rdtype, device=self.device)
 
     def fft_x(self, buf):
+        self._enter()
         self._chk(self.L.psb_slab_fft_x(self.ctx.h, C.byref(self.par), C.byref(self.slab),
                                         buf.data_ptr()), "psb_slab_fft_x")
 
@@ -248,6 +260,7 @@ class GpuSlabEngine:
         nbin = self.nbin()
         pl = t.zeros(nl * nbin, dtype=t.float64, device=self.device)
         il = self.conf.intlace
+        self._enter()
         self._chk(self.L.psb_slab_bin(self.ctx.h, C.byref(self.par), C.byref(self.slab),
                                       fa[0].data_ptr(), fa[1].data_ptr() if il else None,
                                       fb[0].data_ptr(), fb[1].data_ptr() if il else None,
