@@ -186,6 +186,11 @@ psb_result *psb_slab_finish(psb_context *ctx, const psb_params *par, const doubl
  * Returns a device pointer to be released with psb_device_free. */
 double *psb_generate_catalog(psb_context *ctx, size_t n, double boxsize, int kind,
     uint64_t seed);
+/* same, into caller-owned device memory; particle j of the call is particle
+ * first_index + j of the (seed, kind) catalogue, so a catalogue can be produced
+ * in chunks and by several ranks */
+int psb_generate_into(psb_context *ctx, double *dst_dev, size_t n, double boxsize, int kind,
+    uint64_t seed, uint64_t first_index);
 void psb_device_free(psb_context *ctx, void *ptr);
 /* copy device catalogue to host (tests) */
 int psb_copy_to_host(psb_context *ctx, void *dst, const void *src_dev, size_t bytes);

@@ -111,6 +111,7 @@ def load_library():
     L.psb_generate_catalog.restype = C.c_void_p
     L.psb_generate_catalog.argtypes = [C.c_void_p, C.c_size_t, C.c_double, C.c_int, C.c_uint64]
     L.psb_device_free.argtypes = [C.c_void_p, C.c_void_p]
+    L.psb_generate_into.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_int, C.c_uint64, C.c_uint64]
     L.psb_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
     _lib = L
     return L
@@ -354,6 +355,13 @@ class Context:
         if not ptr:
             raise _err(self.L, "psb_generate_catalog")
         return (ptr, n)
+
+    def generate_into(self, tensor, boxsize: float, kind: int = 0, seed: int = 1, first_index: int = 0):
+        """Fill a (n, 4) float64 CUDA tensor with particles first_index.. of the catalogue."""
+        if self.L.psb_generate_into(self.h, tensor.data_ptr(), tensor.shape[0], float(boxsize), int(kind),
+                                    int(seed), int(first_index)):
+            raise _err(self.L, "psb_generate_into")
+        return tensor
 
     def free_catalog(self, cat):
         self.L.psb_device_free(self.h, cat[0])

@@ -1470,6 +1470,15 @@ double *psb_generate_catalog(psb_context *c, size_t n, double boxsize, int kind,
   return (double *) p;
 }
 
+int psb_generate_into(psb_context *c, double *dst_dev, size_t n, double boxsize, int kind, uint64_t seed,
+    uint64_t first_index) {
+  if (!c) { set_error("no device context\n"); return -1; }
+  PSB_CUDA(cudaSetDevice(c->device));
+  if (launch_generate_at(dst_dev, n, boxsize, kind, seed, first_index, c->st)) return -1;
+  PSB_CUDA(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
 void psb_device_free(psb_context *c, void *ptr) {
   if (c) cudaSetDevice(c->device);
   if (ptr) cudaFree(ptr);

@@ -41,9 +41,10 @@ __device__ __forceinline__ double wrap_box(double x, double L) {
 }
 
 __global__ void __launch_bounds__(256) k_generate(double2 *__restrict__ out, size_t n,
-    double L, int kind, uint32_t k0, uint32_t k1) {
-  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n;
-       i += (size_t) gridDim.x * blockDim.x) {
+    double L, int kind, uint32_t k0, uint32_t k1, size_t first) {
+  for (size_t j = blockIdx.x * (size_t) blockDim.x + threadIdx.x; j < n;
+       j += (size_t) gridDim.x * blockDim.x) {
+    const size_t i = first + j;         // global particle index = Philox counter
     const uint32_t ilo = (uint32_t) i, ihi = (uint32_t) (i >> 32);
     const U4 r0 = philox4x32_10({ilo, ihi, 0u, 0u}, k0, k1);
     const U4 r1 = philox4x32_10({ilo, ihi, 1u, 0u}, k0, k1);
@@ -67,22 +68,27 @@ __global__ void __launch_bounds__(256) k_generate(double2 *__restrict__ out, siz
       z = u53(c1.x, c1.y) * L + sigma * rb * cb;
       (void) sb;
     }
-    out[2 * i] = make_double2(wrap_box(x, L), wrap_box(y, L));
-    out[2 * i + 1] = make_double2(wrap_box(z, L), 1.0);
+    out[2 * j] = make_double2(wrap_box(x, L), wrap_box(y, L));
+    out[2 * j + 1] = make_double2(wrap_box(z, L), 1.0);
   }
 }
 
 }  // namespace
 
-int launch_generate(double *out, size_t n, double boxsize, int kind, uint64_t seed,
-    cudaStream_t st) {
+int launch_generate_at(double *out, size_t n, double boxsize, int kind, uint64_t seed,
+    uint64_t first_index, cudaStream_t st) {
   if (!n) return 0;
   size_t b = (n + 255) / 256;
   if (b > 148 * 32) b = 148 * 32;
   k_generate<<<(int) b, 256, 0, st>>>(reinterpret_cast<double2 *>(out), n, boxsize, kind,
-      (uint32_t) seed, (uint32_t) (seed >> 32));
+      (uint32_t) seed, (uint32_t) (seed >> 32), (size_t) first_index);
   PSB_CUDA(cudaGetLastError());
   return 0;
+}
+
+int launch_generate(double *out, size_t n, double boxsize, int kind, uint64_t seed,
+    cudaStream_t st) {
+  return launch_generate_at(out, n, boxsize, kind, seed, 0, st);
 }
 
 }  // namespace psb

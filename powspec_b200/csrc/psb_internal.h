@@ -112,5 +112,7 @@ int launch_scale(void *mesh, size_t n, double factor, int precision, cudaStream_
 // generate.cu
 int launch_generate(double *out, size_t n, double boxsize, int kind, uint64_t seed,
     cudaStream_t st);
+int launch_generate_at(double *out, size_t n, double boxsize, int kind, uint64_t seed,
+    uint64_t first_index, cudaStream_t st);
 
 }  // namespace psb

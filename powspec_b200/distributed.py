@@ -19,10 +19,11 @@ of libpowspec_b200.so (`psb_slab_*`, include/powspec_b200.h):
 The result stays in the transposed (y-slab) layout: binning is layout-agnostic,
 so no transpose back.
 
-The orchestration (`SlabDriver`) is written against two small interfaces — a
-communicator and a per-rank "engine" — so that the same code runs
+The orchestration (`density_to_kspace`, `slab_power`) is written against two
+small interfaces — a communicator and a per-rank "engine" — so that the same
+code runs
   * on N GPUs (`TorchComm` + `GpuSlabEngine`),
-  * emulated on one GPU with N virtual ranks (`LocalComm`; GPU tests), and
+  * emulated on one GPU with N virtual ranks (`slab_power_emulated`; GPU tests), and
   * on CPU with gloo and a numpy engine (tests/test_distributed_cpu.py), which
     checks the exchange logic (split sizes, neighbours, transpose layout).
 """
@@ -213,19 +214,23 @@ class GpuSlabEngine:
                   "psb_slab_partition")
         return out.reshape(-1), [int(c) for c in counts]
 
-    # assign: returns the slab buffers [field] as (planes, ng, rowlen) tensors
-    def assign(self, particles_flat):
+    # slab buffers [field] as (planes, ng, rowlen) tensors, zeroed
+    def alloc_meshes(self):
         t, s = self.torch, self.shape
-        self._enter()
-        n = particles_flat.numel() // 4
         nf = 2 if self.conf.intlace else 1
-        meshes = [t.zeros((s.planes, s.ng, s.rowlen), dtype=self.rdtype, device=self.device)
-                  for _ in range(nf)]
+        return [t.zeros((s.planes, s.ng, s.rowlen), dtype=self.rdtype, device=self.device)
+                for _ in range(nf)]
+
+    # scatter routed particles (flat n*4 tensor) into the slab buffers (accumulates)
+    def assign_into(self, meshes, particles_flat):
+        n = particles_flat.numel() // 4
+        if n == 0:
+            return
+        self._enter()
         self._chk(self.L.psb_slab_assign(self.ctx.h, C.byref(self.par), C.byref(self.slab),
                                          particles_flat.data_ptr(), n, 1.0, meshes[0].data_ptr(),
-                                         meshes[1].data_ptr() if nf == 2 else None),
+                                         meshes[1].data_ptr() if len(meshes) == 2 else None),
                   "psb_slab_assign")
-        return meshes
 
     def add_into(self, dst, src):
         self._enter()
@@ -319,20 +324,35 @@ class GpuSlabEngine:
 # ---------------------------------------------------------------------------
 # the orchestration, shared by all back ends
 # ---------------------------------------------------------------------------
-def density_to_kspace(engine, comm, particles):
-    """One catalogue: local particles (n, 4) -> list over fields of this rank's
-    y-slab of delta(k), shape (Ng_x, ny, Ngk) complex, flattened."""
-    s = engine.shape
-    # 1. route the particles to the owner of their base x-cell
-    sorted_p, counts = engine.partition(particles)
-    if comm.size > 1:
-        mine, _ = comm.all_to_all_v(sorted_p, counts, 4)
+def _chunks(particles):
+    """A catalogue is a (n, 4) tensor or an iterable of such chunks (catalogues
+    larger than one GPU's memory are generated / read chunk by chunk)."""
+    if hasattr(particles, "shape"):
+        yield particles
     else:
-        mine = sorted_p
-    # 2. scatter into the slab buffer (owned planes + halo planes)
-    meshes = engine.assign(mine)
+        yield from particles
+
+
+def density_to_kspace(engine, comm, particles):
+    """One catalogue: this rank's particles (any distribution; a tensor or an
+    iterable of chunks) -> list over fields of this rank's y-slab of delta(k),
+    shape (Ng_x, ny, Ngk) complex, flattened."""
+    s = engine.shape
+    meshes = engine.alloc_meshes()
+    for chunk in _chunks(particles):
+        # 1. route the particles to the owner of their base x-cell
+        sorted_p, counts = engine.partition(chunk)
+        if comm.size > 1:
+            mine, _ = comm.all_to_all_v(sorted_p, counts, 4)
+        else:
+            mine = sorted_p
+        del sorted_p
+        # 2. scatter into the slab buffer (owned planes + halo planes)
+        engine.assign_into(meshes, mine)
+        del mine
     out = []
-    for mesh in meshes:
+    while meshes:
+        mesh = meshes.pop(0)
         # 3. halo planes go to their owners and are added there
         if comm.size > 1:
             to_prev = mesh[0:HALO_LO].contiguous()
@@ -342,9 +362,11 @@ def density_to_kspace(engine, comm, particles):
             engine.add_into(mesh[s.lo:s.lo + HALO_HI], from_prev)
         # 4./5. 2-D FFT of the owned planes, pack, transpose
         send = engine.fft_yz_pack(mesh)
+        del mesh                # the slab buffer is free once packed
         if comm.size > 1:
             recv = engine.empty_like_send()
             comm.all_to_all(recv, send)
+            del send
         else:
             recv = send
         # 6. 1-D FFT along x on the y-slab
@@ -394,7 +416,9 @@ def slab_power_emulated(engines, catalogues_per_rank, wdata, isauto=None, iscros
                 off = sum(cnt[:r]) * 4
                 chunks.append(sp[off:off + cnt[r] * 4])
             mine.append(torch.cat(chunks))
-        meshes = [engines[r].assign(mine[r]) for r in range(G)]
+        meshes = [engines[r].alloc_meshes() for r in range(G)]
+        for r in range(G):
+            engines[r].assign_into(meshes[r], mine[r])
         nf = len(meshes[0])
         fk_c = [[None] * nf for _ in range(G)]
         for f in range(nf):

@@ -32,10 +32,14 @@ class NumpyEngine:
         counts = [int((owner == r).sum()) for r in range(self.shape.nranks)]
         return torch.from_numpy(p[order].copy().reshape(-1)), counts
 
-    def assign(self, flat):
+    def alloc_meshes(self):
+        s = self.shape
+        return [torch.zeros((s.planes, s.ng, s.rowlen), dtype=torch.float64)]
+
+    def assign_into(self, meshes, flat):
         s = self.shape
         p = flat.numpy().reshape(-1, 4)
-        mesh = np.zeros((s.planes, s.ng, s.rowlen))
+        mesh = meshes[0].numpy()
         xbase = 0 if s.nranks == 1 else (s.rank * s.nx - HALO_LO) % NG
         t = p[:, :3] * NG / L
         c = np.floor(t).astype(int)
@@ -48,7 +52,6 @@ class NumpyEngine:
                     lp = ((c[:, 0] + a) % NG - xbase) % NG
                     assert lp.max(initial=0) < s.planes
                     np.add.at(mesh, (lp, (c[:, 1] + b) % NG, (c[:, 2] + e) % NG), w)
-        return [torch.from_numpy(mesh)]
 
     def add_into(self, dst, src):
         dst += src
@@ -75,8 +78,9 @@ class NumpyEngine:
 def _full_reference(parts):
     p = np.concatenate(parts)
     eng = NumpyEngine(1, 0)
-    mesh = eng.assign(torch.from_numpy(p.reshape(-1)))[0].numpy()[:, :, :NG]
-    return np.fft.rfftn(mesh)
+    meshes = eng.alloc_meshes()
+    eng.assign_into(meshes, torch.from_numpy(p.reshape(-1)))
+    return np.fft.rfftn(meshes[0].numpy()[:, :, :NG])
 
 
 def _catalogue(rank):
@@ -92,7 +96,8 @@ def _worker(rank, world, port, q):
     try:
         comm = TorchComm()
         eng = NumpyEngine(world, rank)
-        fk = density_to_kspace(eng, comm, torch.from_numpy(_catalogue(rank)))[0]
+        cat = torch.from_numpy(_catalogue(rank))
+        fk = density_to_kspace(eng, comm, [cat[:1500], cat[1500:1500], cat[1500:]])[0]     # chunked
         got = fk.numpy().view(np.complex128).reshape(NG, eng.shape.nx, eng.shape.ngk)
         want = _full_reference([_catalogue(r) for r in range(world)])
         want = want[:, rank * eng.shape.nx:(rank + 1) * eng.shape.nx, :]
