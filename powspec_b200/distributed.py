@@ -174,6 +174,7 @@ class GpuSlabEngine:
         self.slab = _Slab(nranks, rank)
         self.device = torch.device("cuda", ctx.device)
         self.rdtype = torch.float64 if conf.precision == 8 else torch.float32
+        self._cache = {}
         L = self.L
         if not hasattr(L, "_slab_ready"):
             vp, P, S = C.c_void_p, C.POINTER(type(self.par)), C.POINTER(_Slab)
@@ -214,12 +215,28 @@ class GpuSlabEngine:
                   "psb_slab_partition")
         return out.reshape(-1), [int(c) for c in counts]
 
-    # slab buffers [field] as (planes, ng, rowlen) tensors, zeroed
-    def alloc_meshes(self):
-        t, s = self.torch, self.shape
+    # Persistent buffers: the slab buffers (one set per catalogue) double as the
+    # receive buffers of the transpose (their content is dead once packed), and
+    # one send buffer is shared by all fields.  Nothing of this size is allocated
+    # or freed inside a run, so the peak footprint is fixed:
+    #   ncat * nfields * (nx + halos) planes  +  one packed field.
+    def _cached(self, key, shape, dtype):
+        t = self.torch
+        buf = self._cache.get(key)
+        if buf is None or tuple(buf.shape) != tuple(shape) or buf.dtype != dtype:
+            self._cache[key] = buf = t.empty(shape, dtype=dtype, device=self.device)
+        return buf
+
+    def alloc_meshes(self, cat=0):
+        """slab buffers [field] as (planes, ng, rowlen) tensors, zeroed"""
+        s = self.shape
         nf = 2 if self.conf.intlace else 1
-        return [t.zeros((s.planes, s.ng, s.rowlen), dtype=self.rdtype, device=self.device)
-                for _ in range(nf)]
+        out = []
+        for f in range(nf):
+            m = self._cached(("mesh", cat, f), (s.planes, s.ng, s.rowlen), self.rdtype)
+            m.zero_()
+            out.append(m)
+        return out
 
     # scatter routed particles (flat n*4 tensor) into the slab buffers (accumulates)
     def assign_into(self, meshes, particles_flat):
@@ -237,21 +254,25 @@ class GpuSlabEngine:
         self._chk(self.L.psb_add(self.ctx.h, dst.data_ptr(), src.data_ptr(), src.numel(),
                                  self.conf.precision), "psb_add")
 
-    # 2-D FFT on owned planes + pack for the transpose; returns the send buffer
+    # 2-D FFT on owned planes + pack for the transpose; returns the send buffer.
+    # A single rank needs no transpose: (x-slab, y, k) is already (x, y-slab, k).
     def fft_yz_pack(self, mesh):
-        t, s = self.torch, self.shape
+        s = self.shape
         self._enter()
         owned = mesh[s.lo:s.lo + s.nx]
         self._chk(self.L.psb_slab_fft_yz(self.ctx.h, C.byref(self.par), C.byref(self.slab),
                                          owned.data_ptr()), "psb_slab_fft_yz")
-        send = t.empty(s.nx * s.ng * s.ngk * 2, dtype=self.rdtype, device=self.device)
+        if s.nranks == 1:
+            return mesh.reshape(-1)
+        send = self._cached("send", (s.nx * s.ng * s.ngk * 2,), self.rdtype)
         self._chk(self.L.psb_slab_pack(self.ctx.h, C.byref(self.par), C.byref(self.slab),
                                        owned.data_ptr(), send.data_ptr()), "psb_slab_pack")
         return send
 
-    def empty_like_send(self):
+    def recv_view(self, mesh):
+        """The transpose is received into the slab buffer it came from."""
         s = self.shape
-        return self.torch.empty(s.nx * s.ng * s.ngk * 2, dtype=self.rdtype, device=self.device)
+        return mesh.reshape(-1)[:s.nx * s.ng * s.ngk * 2]
 
     def fft_x(self, buf):
         self._enter()
@@ -333,12 +354,12 @@ def _chunks(particles):
         yield from particles
 
 
-def density_to_kspace(engine, comm, particles):
+def density_to_kspace(engine, comm, particles, cat=0):
     """One catalogue: this rank's particles (any distribution; a tensor or an
     iterable of chunks) -> list over fields of this rank's y-slab of delta(k),
     shape (Ng_x, ny, Ngk) complex, flattened."""
     s = engine.shape
-    meshes = engine.alloc_meshes()
+    meshes = engine.alloc_meshes(cat)
     for chunk in _chunks(particles):
         # 1. route the particles to the owner of their base x-cell
         sorted_p, counts = engine.partition(chunk)
@@ -351,8 +372,7 @@ def density_to_kspace(engine, comm, particles):
         engine.assign_into(meshes, mine)
         del mine
     out = []
-    while meshes:
-        mesh = meshes.pop(0)
+    for mesh in meshes:
         # 3. halo planes go to their owners and are added there
         if comm.size > 1:
             to_prev = mesh[0:HALO_LO].contiguous()
@@ -360,13 +380,12 @@ def density_to_kspace(engine, comm, particles):
             from_next, from_prev = comm.halo_exchange(to_prev, to_next)
             engine.add_into(mesh[s.lo + s.nx - HALO_LO:s.lo + s.nx], from_next)
             engine.add_into(mesh[s.lo:s.lo + HALO_HI], from_prev)
-        # 4./5. 2-D FFT of the owned planes, pack, transpose
+        # 4./5. 2-D FFT of the owned planes, pack, transpose (received into the
+        # slab buffer itself: its content is dead once packed)
         send = engine.fft_yz_pack(mesh)
-        del mesh                # the slab buffer is free once packed
         if comm.size > 1:
-            recv = engine.empty_like_send()
+            recv = engine.recv_view(mesh)
             comm.all_to_all(recv, send)
-            del send
         else:
             recv = send
         # 6. 1-D FFT along x on the y-slab
@@ -383,7 +402,7 @@ def slab_power(engine, comm, catalogues, wdata, isauto=None, iscross=None):
         isauto = [True] * nc
     if iscross is None:
         iscross = nc == 2
-    fk = [density_to_kspace(engine, comm, p) for p in catalogues]
+    fk = [density_to_kspace(engine, comm, p, cat=i) for i, p in enumerate(catalogues)]
     pl = [None, None]
     for i in range(nc):
         if isauto[i]:
@@ -416,7 +435,7 @@ def slab_power_emulated(engines, catalogues_per_rank, wdata, isauto=None, iscros
                 off = sum(cnt[:r]) * 4
                 chunks.append(sp[off:off + cnt[r] * 4])
             mine.append(torch.cat(chunks))
-        meshes = [engines[r].alloc_meshes() for r in range(G)]
+        meshes = [engines[r].alloc_meshes(c) for r in range(G)]
         for r in range(G):
             engines[r].assign_into(meshes[r], mine[r])
         nf = len(meshes[0])
@@ -429,10 +448,10 @@ def slab_power_emulated(engines, catalogues_per_rank, wdata, isauto=None, iscros
                     s = engines[r].shape
                     engines[r].add_into(meshes[r][f][s.lo + s.nx - HALO_LO:s.lo + s.nx], halos[(r + 1) % G][0])
                     engines[r].add_into(meshes[r][f][s.lo:s.lo + HALO_HI], halos[(r - 1) % G][1])
-            sends = [engines[r].fft_yz_pack(meshes[r][f]) for r in range(G)]
+            sends = [engines[r].fft_yz_pack(meshes[r][f]).clone() for r in range(G)]
             blk = sends[0].numel() // G
             for r in range(G):
-                recv = torch.cat([sends[q][r * blk:(r + 1) * blk] for q in range(G)])
+                recv = torch.cat([sends[q][r * blk:(r + 1) * blk] for q in range(G)]) if G > 1 else sends[0]
                 engines[r].fft_x(recv)
                 fk_c[r][f] = recv
         for r in range(G):

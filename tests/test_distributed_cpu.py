@@ -32,7 +32,7 @@ class NumpyEngine:
         counts = [int((owner == r).sum()) for r in range(self.shape.nranks)]
         return torch.from_numpy(p[order].copy().reshape(-1)), counts
 
-    def alloc_meshes(self):
+    def alloc_meshes(self, cat=0):
         s = self.shape
         return [torch.zeros((s.planes, s.ng, s.rowlen), dtype=torch.float64)]
 
@@ -65,7 +65,7 @@ class NumpyEngine:
         packed = np.ascontiguousarray(np.stack(blocks))
         return torch.from_numpy(packed.view(np.float64).reshape(-1).copy())
 
-    def empty_like_send(self):
+    def recv_view(self, mesh):
         s = self.shape
         return torch.empty(s.nx * s.ng * s.ngk * 2, dtype=torch.float64)
 
