@@ -181,6 +181,8 @@ def bench_slab(args, ctx, conf, w, world, rank, local_rank, config, barrier):
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
+    from powspec_b200.distributed import PROF
+    PROF.t.clear()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -192,6 +194,10 @@ def bench_slab(args, ctx, conf, w, world, rank, local_rank, config, barrier):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item()) / args.steps
     if rank == 0:
+        if PROF.on:
+            nrun = args.steps
+            print("slab stage profile (ms per step, rank 0):",
+                  {k: round(1e3 * v / nrun, 2) for k, v in PROF.t.items()}, file=sys.stderr)
         config = dict(config)
         config["parallelism"] = f"one {w['ng']}^3 mesh x-slab-decomposed over {world} GPU(s)"
         config["npart_total"] = n_loc * world

@@ -375,28 +375,28 @@ __device__ __forceinline__ void scatter_coop(const double x[3], double pw, const
   }
 }
 
-constexpr int COOP_ITER = 1;    // particle groups per warp (4 was measured slower: 80 regs, lower occupancy)
-
-template <int SCHEME, typename real, bool INTERLACE>
-__global__ void __launch_bounds__(256) k_assign_coop(const double2 *__restrict__ p, size_t n,
-    AssignGeom g, double wscale, real *__restrict__ mesh0, real *__restrict__ mesh1) {
+// COOP_ITER particle groups per warp (loads issued up front), BLOCK threads per
+// block, MINB blocks per SM for the register allocator.  Variants are selected
+// at run time (option "coop_variant") for ablation; the default is the one
+// measured fastest on B200 for TSC + interlacing.
+template <int SCHEME, typename real, bool INTERLACE, int ITER, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) k_assign_coop(const double2 *__restrict__ p,
+    size_t n, AssignGeom g, double wscale, real *__restrict__ mesh0, real *__restrict__ mesh1) {
   constexpr int NZ = SCHEME + 1;
   constexpr int PPW = 32 / NZ;                  // particles per warp and iteration
   const int lane = threadIdx.x & 31;
   const int sub = lane / NZ, zsel = lane - sub * NZ;
-  const size_t warp = blockIdx.x * (size_t) (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const size_t first = warp * (PPW * COOP_ITER) + sub;
-  // all loads of the warp's COOP_ITER groups are in flight before the first
-  // reduction is issued (the NZ lanes of a particle load the same 32 bytes: one
-  // broadcast request)
-  double2 a[COOP_ITER], b[COOP_ITER];
+  const size_t warp = blockIdx.x * (size_t) (BLOCK >> 5) + (threadIdx.x >> 5);
+  const size_t first = warp * (PPW * ITER) + sub;
+  // the NZ lanes of a particle load the same 32 bytes: one broadcast request
+  double2 a[ITER], b[ITER];
 #pragma unroll
-  for (int it = 0; it < COOP_ITER; it++) {
+  for (int it = 0; it < ITER; it++) {
     const size_t i = first + (size_t) it * PPW;
     if (sub < PPW && i < n) { a[it] = __ldg(p + 2 * i); b[it] = __ldg(p + 2 * i + 1); }
   }
 #pragma unroll
-  for (int it = 0; it < COOP_ITER; it++) {
+  for (int it = 0; it < ITER; it++) {
     const size_t i = first + (size_t) it * PPW;
     if (sub < PPW && i < n) {
       double x[3] = {a[it].x, a[it].y, b[it].x};
@@ -412,22 +412,34 @@ __global__ void __launch_bounds__(256) k_assign_coop(const double2 *__restrict__
   }
 }
 
+template <int SCHEME, typename real, int ITER, int BLOCK, int MINB>
+static int launch_coop_v(const double2 *pp, size_t n, const AssignGeom &g, double wscale, void *m0,
+    void *m1, cudaStream_t st) {
+  constexpr int PPB = (BLOCK / 32) * ITER * (32 / (SCHEME + 1));   // particles per block
+  const size_t nb = (n + PPB - 1) / PPB;
+  if (nb > 0x7fffffffull) { set_error("too many particles in one assignment chunk\n"); return -1; }
+  if (m1)
+    k_assign_coop<SCHEME, real, true, ITER, BLOCK, MINB><<<(int) nb, BLOCK, 0, st>>>(pp, n, g, wscale,
+        static_cast<real *>(m0), static_cast<real *>(m1));
+  else
+    k_assign_coop<SCHEME, real, false, ITER, BLOCK, MINB><<<(int) nb, BLOCK, 0, st>>>(pp, n, g, wscale,
+        static_cast<real *>(m0), nullptr);
+  PSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 template <int SCHEME, typename real>
 static int launch_assign_t(const double *p, size_t n, const AssignGeom &g, double wscale,
     void *m0, void *m1, cudaStream_t st) {
   const double2 *pp = reinterpret_cast<const double2 *>(p);
   if (g.coop && SCHEME > 0) {
-    constexpr int PPB = 8 * COOP_ITER * (32 / (SCHEME + 1));    // particles per 256-thread block
-    const size_t nb = (n + PPB - 1) / PPB;
-    if (nb > 0x7fffffffull) { set_error("too many particles in one assignment chunk\n"); return -1; }
-    if (m1)
-      k_assign_coop<SCHEME, real, true><<<(int) nb, 256, 0, st>>>(pp, n, g, wscale,
-          static_cast<real *>(m0), static_cast<real *>(m1));
-    else
-      k_assign_coop<SCHEME, real, false><<<(int) nb, 256, 0, st>>>(pp, n, g, wscale,
-          static_cast<real *>(m0), nullptr);
-    PSB_CUDA(cudaGetLastError());
-    return 0;
+    switch (g.coop_variant) {
+      case 1: return launch_coop_v<SCHEME, real, 1, 128, 8>(pp, n, g, wscale, m0, m1, st);
+      case 2: return launch_coop_v<SCHEME, real, 2, 256, 4>(pp, n, g, wscale, m0, m1, st);
+      case 3: return launch_coop_v<SCHEME, real, 1, 256, 6>(pp, n, g, wscale, m0, m1, st);
+      case 4: return launch_coop_v<SCHEME, real, 2, 128, 8>(pp, n, g, wscale, m0, m1, st);
+      default: return launch_coop_v<SCHEME, real, 1, 256, 1>(pp, n, g, wscale, m0, m1, st);
+    }
   }
   const size_t nblk = (n + 255) / 256;
   if (nblk > 0x7fffffffull) { set_error("too many particles in one assignment chunk\n"); return -1; }
@@ -489,6 +501,50 @@ int launch_owner_keys(const double *p, size_t n, const AssignGeom &g, int nranks
   if (nranks > 64) { set_error("at most 64 slabs are supported\n"); return -1; }
   k_owner_keys<<<grid_for(n, 256, 148 * 16), 256, 0, st>>>(
       reinterpret_cast<const double2 *>(p), n, g, nranks, keys, hist);
+  PSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Block-aggregated partition by owner: with at most 64 destinations a plain
+// per-particle atomic cursor serialises on 2..64 addresses.  Each block counts
+// its particles per destination in shared memory, reserves one contiguous range
+// per destination with a single global atomic, and fills it.
+constexpr int OWN_PER_THREAD = 8;
+__global__ void __launch_bounds__(256) k_owner_scatter(const double2 *__restrict__ p, size_t n,
+    const uint32_t *__restrict__ keys, uint32_t *__restrict__ cursor, int nranks,
+    double2 *__restrict__ out) {
+  __shared__ uint32_t cnt[64], base[64];
+  if (threadIdx.x < 64) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const size_t tile = (size_t) blockIdx.x * (256 * OWN_PER_THREAD);
+  uint32_t key[OWN_PER_THREAD], slot[OWN_PER_THREAD];
+#pragma unroll
+  for (int q = 0; q < OWN_PER_THREAD; q++) {
+    const size_t i = tile + (size_t) q * 256 + threadIdx.x;
+    key[q] = 0xffffffffu;
+    if (i < n) { key[q] = keys[i]; slot[q] = atomicAdd(&cnt[key[q]], 1u); }
+  }
+  __syncthreads();
+  if (threadIdx.x < nranks && cnt[threadIdx.x])
+    base[threadIdx.x] = atomicAdd(cursor + threadIdx.x, cnt[threadIdx.x]);
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < OWN_PER_THREAD; q++) {
+    const size_t i = tile + (size_t) q * 256 + threadIdx.x;
+    if (i < n) {
+      const size_t pos = (size_t) base[key[q]] + slot[q];
+      out[2 * pos] = __ldg(p + 2 * i);
+      out[2 * pos + 1] = __ldg(p + 2 * i + 1);
+    }
+  }
+}
+
+int launch_owner_scatter(const double *p, size_t n, const uint32_t *keys, uint32_t *cursor,
+    int nranks, double *sorted, cudaStream_t st) {
+  if (!n) return 0;
+  const size_t nb = (n + 256 * OWN_PER_THREAD - 1) / (256 * OWN_PER_THREAD);
+  k_owner_scatter<<<(unsigned) nb, 256, 0, st>>>(reinterpret_cast<const double2 *>(p), n, keys,
+      cursor, nranks, reinterpret_cast<double2 *>(sorted));
   PSB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -141,6 +141,7 @@ struct psb_context {
   long opt_sort_min = 1 << 16;
   long opt_geom_sym = 1;                // fold +-n_x, +-n_y in the mode-counting pass
   long opt_coop = 1;                    // z-coalesced scatter kernel
+  long opt_coop_variant = 0;
   long opt_strip = 64;                  // rows per strip of the sort order
   long opt_stream = 1;                  // overlap H2D with assignment for host catalogues (sims)
   long opt_stream_chunk = 1 << 24;      // particles per streamed chunk (512 MiB)
@@ -842,6 +843,7 @@ int psb_set_option(psb_context *c, const char *name, long value) {
   if (!strcmp(name, "sort_min")) { c->opt_sort_min = value; return 0; }
   if (!strcmp(name, "strip")) { c->opt_strip = value; return 0; }
   if (!strcmp(name, "coop")) { c->opt_coop = value; return 0; }
+  if (!strcmp(name, "coop_variant")) { c->opt_coop_variant = value; return 0; }
   if (!strcmp(name, "geom_sym")) { c->opt_geom_sym = value; return 0; }
   if (!strcmp(name, "stream")) { c->opt_stream = value; return 0; }
   if (!strcmp(name, "stream_chunk")) { c->opt_stream_chunk = value; return 0; }
@@ -908,6 +910,7 @@ int psb_mesh(psb_context *c, const psb_params *par, const psb_cats *cats) {
   g.ng = ng; g.rowlen = rowlen;
   g.strip = (int) std::min<long>(std::max<long>(c->opt_strip, 1), ng);
   g.coop = (int) c->opt_coop;
+  g.coop_variant = (int) c->opt_coop_variant;
   g.x0 = 0; g.nx = ng; g.xbase = 0; g.nxloc = ng;
   for (int a = 0; a < 3; a++) {
     g.org[a] = c->bmin[a];
@@ -1245,6 +1248,7 @@ static int slab_geom(psb_context *c, const psb_params *par, const psb_slab *sl, 
   g.ng = ng; g.rowlen = 2 * (ng / 2 + 1);
   g.strip = (int) std::min<long>(std::max<long>(c->opt_strip, 1), ng);
   g.coop = (int) c->opt_coop;
+  g.coop_variant = (int) c->opt_coop_variant;
   g.x0 = sl->rank * nx; g.nx = nx;
   if (sl->nranks == 1) { g.xbase = 0; g.nxloc = ng; }
   else { g.xbase = (g.x0 - PSB_HALO_LO + ng) % ng; g.nxloc = nx + PSB_HALO_LO + PSB_HALO_HI; }
@@ -1285,7 +1289,8 @@ int psb_slab_partition(psb_context *c, const psb_params *par, int nranks, const 
   uint32_t cur[64], acc = 0;
   for (int r = 0; r < 64; r++) { cur[r] = acc; if (r < nranks) { counts[r] = h[r]; acc += h[r]; } }
   PSB_CUDA(cudaMemcpyAsync(c->cursor.p, cur, 64 * 4, cudaMemcpyHostToDevice, c->st));
-  if (launch_row_scatter(particles, n, c->keys.as<uint32_t>(), c->cursor.as<uint32_t>(), sorted, c->st))
+  if (launch_owner_scatter(particles, n, c->keys.as<uint32_t>(), c->cursor.as<uint32_t>(), nranks, sorted,
+        c->st))
     return -1;
   PSB_CUDA(cudaStreamSynchronize(c->st));
   c->launches += 2;

@@ -33,6 +33,7 @@ struct AssignGeom {
   int rowlen;           // reals per z-row of the (padded, in-place FFT) mesh
   int strip;            // rows per strip of the sort order (row-key layout)
   int coop;             // z-coalesced scatter (NZ lanes per particle)
+  int coop_variant;     // launch shape of the z-coalesced kernel (ablation)
   int x0, nx;           // owned x-planes [x0, x0+nx) (single GPU: 0, Ng)
   int xbase, nxloc;     // planes held by the local buffer: xbase .. xbase+nxloc-1 (mod Ng)
   double org[3];        // lower box corner (MESH.min)
@@ -57,6 +58,8 @@ int launch_unpad_copy(const void *mesh, void *dst, int ng, int rowlen,
     int precision, cudaStream_t st);
 int launch_owner_keys(const double *p, size_t n, const AssignGeom &g, int nranks,
     uint32_t *keys, uint32_t *hist, cudaStream_t st);
+int launch_owner_scatter(const double *p, size_t n, const uint32_t *keys, uint32_t *cursor,
+    int nranks, double *sorted, cudaStream_t st);
 int launch_add(void *dst, const void *src, size_t n, int precision, cudaStream_t st);
 
 // ---------------------------------------------------------------------------

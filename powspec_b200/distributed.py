@@ -345,6 +345,42 @@ class GpuSlabEngine:
 # ---------------------------------------------------------------------------
 # the orchestration, shared by all back ends
 # ---------------------------------------------------------------------------
+class _Prof:
+    """Optional host-side stage timers (PSB_SLAB_PROFILE=1): device-synchronised
+    wall time per stage, accumulated per process; for development only."""
+
+    def __init__(self):
+        import os
+        self.on = bool(os.environ.get("PSB_SLAB_PROFILE"))
+        self.t = {}
+
+    def __call__(self, name):
+        prof = self
+
+        class _S:
+            def __enter__(self_):
+                if prof.on:
+                    import time
+
+                    import torch
+                    if torch.cuda.is_available():
+                        torch.cuda.synchronize()
+                    self_.t0 = time.perf_counter()
+
+            def __exit__(self_, *a):
+                if prof.on:
+                    import time
+
+                    import torch
+                    if torch.cuda.is_available():
+                        torch.cuda.synchronize()
+                    prof.t[name] = prof.t.get(name, 0.0) + time.perf_counter() - self_.t0
+        return _S()
+
+
+PROF = _Prof()
+
+
 def _chunks(particles):
     """A catalogue is a (n, 4) tensor or an iterable of such chunks (catalogues
     larger than one GPU's memory are generated / read chunk by chunk)."""
@@ -359,37 +395,45 @@ def density_to_kspace(engine, comm, particles, cat=0):
     iterable of chunks) -> list over fields of this rank's y-slab of delta(k),
     shape (Ng_x, ny, Ngk) complex, flattened."""
     s = engine.shape
-    meshes = engine.alloc_meshes(cat)
+    with PROF("zero_meshes"):
+        meshes = engine.alloc_meshes(cat)
     for chunk in _chunks(particles):
         # 1. route the particles to the owner of their base x-cell
-        sorted_p, counts = engine.partition(chunk)
-        if comm.size > 1:
-            mine, _ = comm.all_to_all_v(sorted_p, counts, 4)
-        else:
-            mine = sorted_p
+        with PROF("partition"):
+            sorted_p, counts = engine.partition(chunk)
+        with PROF("route_a2av"):
+            if comm.size > 1:
+                mine, _ = comm.all_to_all_v(sorted_p, counts, 4)
+            else:
+                mine = sorted_p
         del sorted_p
         # 2. scatter into the slab buffer (owned planes + halo planes)
-        engine.assign_into(meshes, mine)
+        with PROF("assign"):
+            engine.assign_into(meshes, mine)
         del mine
     out = []
     for mesh in meshes:
         # 3. halo planes go to their owners and are added there
         if comm.size > 1:
-            to_prev = mesh[0:HALO_LO].contiguous()
-            to_next = mesh[s.lo + s.nx:s.lo + s.nx + HALO_HI].contiguous()
-            from_next, from_prev = comm.halo_exchange(to_prev, to_next)
-            engine.add_into(mesh[s.lo + s.nx - HALO_LO:s.lo + s.nx], from_next)
-            engine.add_into(mesh[s.lo:s.lo + HALO_HI], from_prev)
+            with PROF("halo"):
+                to_prev = mesh[0:HALO_LO].contiguous()
+                to_next = mesh[s.lo + s.nx:s.lo + s.nx + HALO_HI].contiguous()
+                from_next, from_prev = comm.halo_exchange(to_prev, to_next)
+                engine.add_into(mesh[s.lo + s.nx - HALO_LO:s.lo + s.nx], from_next)
+                engine.add_into(mesh[s.lo:s.lo + HALO_HI], from_prev)
         # 4./5. 2-D FFT of the owned planes, pack, transpose (received into the
         # slab buffer itself: its content is dead once packed)
-        send = engine.fft_yz_pack(mesh)
-        if comm.size > 1:
-            recv = engine.recv_view(mesh)
-            comm.all_to_all(recv, send)
-        else:
-            recv = send
+        with PROF("fft_yz_pack"):
+            send = engine.fft_yz_pack(mesh)
+        with PROF("transpose_a2a"):
+            if comm.size > 1:
+                recv = engine.recv_view(mesh)
+                comm.all_to_all(recv, send)
+            else:
+                recv = send
         # 6. 1-D FFT along x on the y-slab
-        engine.fft_x(recv)
+        with PROF("fft_x"):
+            engine.fft_x(recv)
         out.append(recv)
     return out
 
@@ -404,15 +448,17 @@ def slab_power(engine, comm, catalogues, wdata, isauto=None, iscross=None):
         iscross = nc == 2
     fk = [density_to_kspace(engine, comm, p, cat=i) for i, p in enumerate(catalogues)]
     pl = [None, None]
-    for i in range(nc):
-        if isauto[i]:
-            pl[i] = comm.all_reduce_sum(engine.bin(fk[i], fk[i])) if comm.size > 1 else engine.bin(fk[i], fk[i])
-    xpl = None
-    if iscross and nc == 2:
-        xpl = engine.bin(fk[0], fk[1])
-        if comm.size > 1:
-            xpl = comm.all_reduce_sum(xpl)
-    return engine.finish(pl, xpl, wdata)
+    with PROF("bin_allreduce"):
+        for i in range(nc):
+            if isauto[i]:
+                pl[i] = comm.all_reduce_sum(engine.bin(fk[i], fk[i])) if comm.size > 1 else engine.bin(fk[i], fk[i])
+        xpl = None
+        if iscross and nc == 2:
+            xpl = engine.bin(fk[0], fk[1])
+            if comm.size > 1:
+                xpl = comm.all_reduce_sum(xpl)
+    with PROF("finish"):
+        return engine.finish(pl, xpl, wdata)
 
 
 # ---------------------------------------------------------------------------
