@@ -364,9 +364,17 @@ def main():
     b_fft = F * 3 * (ntot * s_real + ncmplx * 2 * s_real)
     t_assign = stages.get("assign", 0.0) * 1e-3
     ach = b_assign / t_assign / 1e9 if t_assign > 0 else 0.0
-    roofline = {"kernel": "k_assign<TSC,double,interlaced> (mass assignment, both fields)",
+    # DRAM traffic of the kernel per launch from the committed ncu --set full capture
+    # (profiles/r1_v4_ncu_k_assign_coop.txt: dram__bytes_read 21.01 GB + write 17.55 GB);
+    # only valid for the workload it was captured on
+    traffic = 38.56e9 if (args.workload == "c2" and not (args.npart or args.ng or args.opt)
+                          and args.precision == 8) else None
+    roofline = {"kernel": "k_assign_coop<%s,%s,%s> (mass assignment, %d field(s))" % (
+                    w["assign"], "double" if args.precision == 8 else "float",
+                    "interlaced" if w["interlace"] else "single", F),
                 "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "peak_source": peak_src, "traffic": None,
+                "frac": ach / peak, "peak_source": peak_src, "traffic": traffic,
+                "limiter": "L2 sector-request rate of the fp64 reductions (ncu lts__throughput 68 %), not HBM",
                 "algorithmic_bytes": b_assign, "launch_ms": stages.get("assign", 0.0),
                 "other_stages": {
                     "fft": {"ms": stages.get("fft", 0.0), "algorithmic_bytes": b_fft,

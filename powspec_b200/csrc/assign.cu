@@ -25,6 +25,13 @@
 
 namespace psb {
 
+static int grid_for(size_t n, int per_block, int max_blocks) {
+  size_t b = (n + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > (size_t) max_blocks) b = max_blocks;
+  return (int) b;
+}
+
 // ---------------------------------------------------------------------------
 // bounds: per-block partial min/max of the three coordinates
 // ---------------------------------------------------------------------------
@@ -79,18 +86,31 @@ __device__ __forceinline__ int base_cell(double t, int ng) {
   // quirk Q8: a coordinate that rounds to t == Ng indexes out
   // of bounds in the reference; wrap it instead
   if (c >= ng) c -= ng;
-  if (c < 0) c = 0;
-  return c;
+  // coordinates outside the box are rejected by def_box's checks (evaluated
+  // after the scatter for simulation boxes): never index out of bounds meanwhile
+  return min(max(c, 0), ng - 1);
 }
 
 // ---------------------------------------------------------------------------
 // counting sort by the (x,y) row of the base cell on the unshifted grid
 // ---------------------------------------------------------------------------
+// `partials` (optional, [gridDim.x][6]): per-block min/max of the coordinates,
+// so that simulation boxes get def_box's bound checks without a separate pass
+// over the catalogue (the record is one 32-byte sector: z comes for free).
 __global__ void __launch_bounds__(256) k_row_keys(const double2 *__restrict__ p,
-    size_t n, AssignGeom g, uint32_t *__restrict__ keys, uint32_t *__restrict__ hist) {
+    size_t n, AssignGeom g, uint32_t *__restrict__ keys, uint32_t *__restrict__ hist,
+    double *__restrict__ partials) {
+  double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX};
+  double hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
   for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n;
        i += (size_t) gridDim.x * blockDim.x) {
     double2 a = __ldg(p + 2 * i);
+    if (partials) {
+      const double z = __ldg(&p[2 * i + 1].x);
+      lo[0] = fmin(lo[0], a.x); hi[0] = fmax(hi[0], a.x);
+      lo[1] = fmin(lo[1], a.y); hi[1] = fmax(hi[1], a.y);
+      lo[2] = fmin(lo[2], z); hi[2] = fmax(hi[2], z);
+    }
     int cx = base_cell(grid_coord(a.x, g.org[0], g.len[0], g.ng), g.ng);
     int cy = base_cell(grid_coord(a.y, g.org[1], g.len[1], g.ng), g.ng);
     // strip-major row order: the sweep over x stays inside a strip of
@@ -102,6 +122,25 @@ __global__ void __launch_bounds__(256) k_row_keys(const double2 *__restrict__ p,
         * (uint32_t) g.strip + (uint32_t) (cy % g.strip);
     keys[i] = key;
     atomicAdd(hist + key, 1u);
+  }
+  if (!partials) return;
+  __shared__ double s[6][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      lo[a] = fmin(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+      hi[a] = fmax(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+    }
+    if (lane == 0) { s[a][warp] = lo[a]; s[3 + a][warp] = hi[a]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    double v = s[threadIdx.x][0];
+    for (int w = 1; w < 8; w++)
+      v = (threadIdx.x < 3) ? fmin(v, s[threadIdx.x][w]) : fmax(v, s[threadIdx.x][w]);
+    partials[blockIdx.x * 6 + threadIdx.x] = v;
   }
 }
 
@@ -117,22 +156,17 @@ __global__ void __launch_bounds__(256) k_row_scatter(const double2 *__restrict__
   }
 }
 
-static int grid_for(size_t n, int per_block, int max_blocks) {
-  size_t b = (n + per_block - 1) / per_block;
-  if (b < 1) b = 1;
-  if (b > (size_t) max_blocks) b = max_blocks;
-  return (int) b;
-}
-
 size_t row_key_count(const AssignGeom &g) {
   const size_t nstrip = ((size_t) g.ng + g.strip - 1) / g.strip;
   return nstrip * (size_t) g.nx * (size_t) g.strip;
 }
 
+int row_keys_blocks(size_t n) { return grid_for(n, 256, 148 * 16); }
+
 int launch_row_keys(const double *p, size_t n, const AssignGeom &g, uint32_t *keys,
-    uint32_t *hist, cudaStream_t st) {
-  k_row_keys<<<grid_for(n, 256, 148 * 16), 256, 0, st>>>(
-      reinterpret_cast<const double2 *>(p), n, g, keys, hist);
+    uint32_t *hist, double *partials, cudaStream_t st) {
+  k_row_keys<<<row_keys_blocks(n), 256, 0, st>>>(
+      reinterpret_cast<const double2 *>(p), n, g, keys, hist, partials);
   PSB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -160,7 +194,7 @@ __device__ __forceinline__ void axis_stencil(double t, int ng, int (&idx)[SCHEME
   int c = (int) t;
   double d = t - (double) c;    // exact
   if (c >= ng) c -= ng;         // Q8 guard, see base_cell()
-  if (c < 0) c = 0;
+  c = min(max(c, 0), ng - 1);
   if constexpr (SCHEME == 0) {  // NGP, src/genr_mesh.c:60-66
     if (d >= 0.5) c = wrap_up(c, ng);
     idx[0] = c; w[0] = 1.0;
@@ -305,7 +339,7 @@ template <int SCHEME>
 __device__ __forceinline__ void stencil_from(int c, double d, int ng, int (&idx)[SCHEME + 1],
     double (&w)[SCHEME + 1]) {
   if (c >= ng) c -= ng;         // quirk Q8 guard
-  if (c < 0) c = 0;
+  c = min(max(c, 0), ng - 1);   // out-of-box input: stay in bounds, def_box rejects it later
   if constexpr (SCHEME == 0) {
     if (d >= 0.5) c = wrap_up(c, ng);
     idx[0] = c; w[0] = 1.0;

@@ -147,7 +147,16 @@ __global__ void __launch_bounds__(256) k_spectrum(BinGeom g, const void *__restr
       psij = si * cj + ci * sj;
     }
     const size_t rbase = ((size_t) i * g.nj + (j - g.j0)) * (size_t) g.ngk;
+    // Cells beyond the last bin edge (with KMAX at the Nyquist frequency: the
+    // corners of the cube, 48 % of all cells) are never read: along a row k^2
+    // grows with k, so a row whose k = 0 cell is already out is skipped and a
+    // row is left at the first 32-cell chunk that starts out of range.  The
+    // test is the same `k2 < edges[nbin]` that decides the cells one by one.
+    const double k2max = edges[g.nbin], k2min = edges[0];
+    if (!(k2ij < k2max)) continue;
     for (int kb = 0; kb < g.ngk; kb += 32) {
+      if (!(__dadd_rn(k2ij, __ldg(g.kax2[2] + kb)) < k2max)) break;
+      if (__dadd_rn(k2ij, __ldg(g.kax2[2] + min(kb + 31, g.ngk - 1))) < k2min) continue;
       const int k = kb + lane;
       int key = -1;
       double v[NV];

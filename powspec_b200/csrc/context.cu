@@ -111,8 +111,8 @@ struct psb_context {
   DevBuf chunkbuf[2];                   // double-buffered device chunks of a streamed catalogue
   cudaStream_t st_copy = nullptr;       // H2D engine stream of the streaming path
   cudaEvent_t ev_filled[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
-  std::vector<double> bounds_host;      // per-chunk bounds partials of the streaming path
   DevBuf sorted, keys, hist, cursor, cubtmp, bounds_part;
+  size_t bounds_used = 0;               // bytes of bounds_part holding deferred bounds partials
   void *pinned[2] = {nullptr, nullptr};
   size_t pinned_bytes = 0;
   cudaEvent_t pinned_free[2] = {nullptr, nullptr};
@@ -312,10 +312,25 @@ int coordinate_bounds(psb_context *c, const double *dev, size_t n, double lo[3],
 // suffice and the scratch stays bounded.
 // One device-resident chunk: counting sort by mesh row, then the scatter.
 // `consumed` (optional) is recorded once the source buffer is no longer read.
+// `bounds` (optional): the chunk's coordinate bounds are appended to
+// c->bounds_part (6 doubles per block); bounds_finish() reduces them.
 int sort_assign_chunk(psb_context *c, const double *src, size_t len, const AssignGeom &g,
-    int scheme, int precision, double wscale, void *m0, void *m1, cudaEvent_t consumed) {
+    int scheme, int precision, double wscale, void *m0, void *m1, cudaEvent_t consumed,
+    bool bounds = false) {
   if (!len) return 0;
   const bool do_sort = c->opt_sort && len >= (size_t) c->opt_sort_min;
+  double *partials = nullptr;
+  if (bounds) {
+    const int nblk = do_sort ? row_keys_blocks(len) : c->sms * 8;
+    if (c->bounds_part.reserve(c->bounds_used + sizeof(double) * 6 * nblk)) return -1;
+    partials = reinterpret_cast<double *>(c->bounds_part.as<char>() + c->bounds_used);
+    c->bounds_used += sizeof(double) * 6 * nblk;
+    if (!do_sort) {
+      StageScope sc(c, PSB_T_BOUNDS, c->st);
+      if (launch_bounds(src, len, partials, nblk, c->st)) return -1;
+      c->launches++;
+    }
+  }
   if (!do_sort) {
     StageScope sc(c, PSB_T_ASSIGN, c->st);
     c->launches++;
@@ -335,7 +350,7 @@ int sort_assign_chunk(psb_context *c, const double *src, size_t len, const Assig
   {
     StageScope sc(c, PSB_T_SORT, c->st);
     PSB_CUDA(cudaMemsetAsync(c->hist.p, 0, nrow * 4, c->st));
-    if (launch_row_keys(src, len, g, c->keys.as<uint32_t>(), c->hist.as<uint32_t>(), c->st))
+    if (launch_row_keys(src, len, g, c->keys.as<uint32_t>(), c->hist.as<uint32_t>(), partials, c->st))
       return -1;
     PSB_CUDA(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp_bytes, c->hist.as<uint32_t>(),
         c->cursor.as<uint32_t>(), (int) nrow, c->st));
@@ -354,14 +369,40 @@ int sort_assign_chunk(psb_context *c, const double *src, size_t len, const Assig
 
 // A catalogue that is already on the device.  Chunked so that 32-bit offsets
 // suffice and the sort scratch stays bounded.
+const size_t DEV_CHUNK = (size_t) 1 << 28;      // particles per chunk (8.6 GB of records)
+
 int assign_catalog(psb_context *c, const double *dev, size_t n, const AssignGeom &g, int scheme,
-    int precision, double wscale, void *m0, void *m1) {
-  const size_t CH = (size_t) 1 << 28;   // particles per chunk (8.6 GB of records)
-  for (size_t off = 0; off < n; off += CH)
-    if (sort_assign_chunk(c, dev + 4 * off, std::min(CH, n - off), g, scheme, precision, wscale,
-          m0, m1, nullptr))
+    int precision, double wscale, void *m0, void *m1, bool bounds = false) {
+  for (size_t off = 0; off < n; off += DEV_CHUNK)
+    if (sort_assign_chunk(c, dev + 4 * off, std::min(DEV_CHUNK, n - off), g, scheme, precision,
+          wscale, m0, m1, nullptr, bounds))
       return -1;
   return 0;
+}
+
+// room for the deferred bounds partials of `nchunk` chunks
+int bounds_begin(psb_context *c, size_t nchunk) {
+  c->bounds_used = 0;
+  return c->bounds_part.reserve(sizeof(double) * 6 * (size_t) (c->sms * 16 + 64) * (nchunk + 1));
+}
+
+// def_box's checks for simulation boxes (src/genr_mesh.c:516-531), evaluated
+// after the catalogue has been scattered
+int bounds_finish(psb_context *c, const psb_params *par) {
+  std::vector<double> h(c->bounds_used / sizeof(double));
+  if (!h.empty()) {
+    PSB_CUDA(cudaMemcpyAsync(h.data(), c->bounds_part.p, c->bounds_used, cudaMemcpyDeviceToHost, c->st));
+    PSB_CUDA(cudaStreamSynchronize(c->st));
+  }
+  double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+  for (size_t q = 0; q + 5 < h.size(); q += 6)
+    for (int a = 0; a < 3; a++) {
+      lo[a] = std::min(lo[a], h[q + a]);
+      hi[a] = std::max(hi[a], h[q + 3 + a]);
+    }
+  for (int a = 0; a < 3; a++) c->bmax[a] = hi[a];
+  double bmin_chk[3], bsize_chk[3];
+  return define_box(par, lo, hi, bmin_chk, bsize_chk);
 }
 
 // Copy `bytes` from host memory into a device buffer on the copy stream.
@@ -423,16 +464,14 @@ bool is_pinned(const void *p) {
 // A catalogue in HOST memory, box known in advance (simulation boxes): chunks
 // are uploaded on the copy stream while the previous chunk is being sorted and
 // scattered, so PCIe and the SMs work concurrently and the catalogue never has
-// to be resident as a whole.  Bounds partials of every chunk are appended to
-// c->bounds_host (reduced by the caller after the stream has drained).
+// to be resident as a whole.  Bounds partials of every chunk are left on the
+// device (bounds_finish reduces them after the stream has drained).
 int stream_catalog(psb_context *c, const double *host, size_t n, const AssignGeom &g, int scheme,
     int precision, double wscale, void *m0, void *m1) {
   if (!n) return 0;
   const size_t CH = (size_t) std::max<long>(c->opt_stream_chunk, 1 << 16);
   const size_t chunk_max = std::min(n, CH);
-  const int nblk = c->sms * 8;
   const size_t nchunk = (n + CH - 1) / CH;
-  if (c->bounds_part.reserve(sizeof(double) * 6 * nblk * nchunk)) return -1;
   const bool pinned = is_pinned(host);
   for (int s = 0; s < 2; s++) {
     if (nchunk > (size_t) s && c->chunkbuf[s].reserve(chunk_max * 32)) return -1;
@@ -457,21 +496,9 @@ int stream_catalog(psb_context *c, const double *host, size_t n, const AssignGeo
     }
     PSB_CUDA(cudaEventRecord(c->ev_filled[s], c->st_copy));
     PSB_CUDA(cudaStreamWaitEvent(c->st, c->ev_filled[s], 0));
-    {
-      StageScope sc(c, PSB_T_BOUNDS, c->st);
-      if (launch_bounds(buf, len, c->bounds_part.as<double>() + 6 * (size_t) nblk * k, nblk, c->st))
-        return -1;
-      c->launches++;
-    }
-    if (sort_assign_chunk(c, buf, len, g, scheme, precision, wscale, m0, m1, c->ev_consumed[s]))
+    if (sort_assign_chunk(c, buf, len, g, scheme, precision, wscale, m0, m1, c->ev_consumed[s], true))
       return -1;
   }
-  const size_t cur = c->bounds_host.size();
-  c->bounds_host.resize(cur + 6 * (size_t) nblk * nchunk);
-  PSB_CUDA(cudaMemcpyAsync(c->bounds_host.data() + cur, c->bounds_part.p,
-      sizeof(double) * 6 * nblk * nchunk, cudaMemcpyDeviceToHost, c->st));
-  // bounds_part is reused by the next catalogue: drain before returning
-  PSB_CUDA(cudaStreamSynchronize(c->st));
   return 0;
 }
 
@@ -696,7 +723,7 @@ int prepare_bins(psb_context *c, const psb_params *par) {
   // per-axis tables: k, k^2, window, interlace phase (3 x 5 x ng) + k^2 edges
   const size_t tlen = (size_t) ng;
   std::vector<double> &T = c->host_tables;
-  T.assign(15 * tlen + nbin + 1, 0.0);
+  T.assign(15 * tlen + nbin + 1 + 6 * tlen, 0.0);
   const double fac = PI / ng;
   for (int a = 0; a < 3; a++) {
     const double vec = 2 * PI / c->bsize[a];    // src/multipole.c:113
@@ -727,7 +754,18 @@ int prepare_bins(psb_context *c, const psb_params *par) {
       });
     e[nbin] = bisect_first([&](double x) { return coord(x) >= k1; });
   }
-  if (c->tables.reserve(T.size() * sizeof(double))) return -1;
+  {
+    // z-axis tables packed per k for the binning kernel: one address, three 16-byte loads
+    double *zt = &T[15 * tlen + nbin + 1];
+    for (int k = 0; k < ng; k++) {
+      zt[6 * k + 0] = T[(3 + 2) * tlen + k];     // k_z^2
+      zt[6 * k + 1] = T[(6 + 2) * tlen + k];     // window
+      zt[6 * k + 2] = T[(9 + 2) * tlen + k];     // cos(pi k / Ng)
+      zt[6 * k + 3] = T[(12 + 2) * tlen + k];    // sin
+      zt[6 * k + 4] = T[(0 + 2) * tlen + k];     // k_z
+    }
+  }
+  if (c->tables.reserve(T.size() * sizeof(double) + 16)) return -1;
   BinGeom &bg = c->bg;
   memset(&bg, 0, sizeof bg);
   bg.ng = ng; bg.ngk = ngk; bg.nbin = nbin; bg.nl = nl;
@@ -744,6 +782,27 @@ int prepare_bins(psb_context *c, const psb_params *par) {
     bg.pc[a] = base + (9 + a) * tlen; bg.ps[a] = base + (12 + a) * tlen;
   }
   bg.k2edge = c->tables.as<double>() + 15 * tlen;
+  bg.ztab = c->tables.as<double>() + 15 * tlen + nbin + 1;
+  if ((15 * tlen + nbin + 1) & 1) {
+    // keep the packed table 16-byte aligned for the double2 loads
+    T.insert(T.begin() + 15 * tlen + nbin + 1, 0.0);
+    bg.ztab += 1;
+  }
+  {
+    // math/legpoly.h:47-61 as coefficient rows: even: c0 + c1 x^2 + c2 x^4 + c3 x^6,
+    // odd: x * (same form)
+    static const double LC[7][4] = {
+      {1, 0, 0, 0}, {1, 0, 0, 0}, {-0.5, 1.5, 0, 0}, {-1.5, 2.5, 0, 0},
+      {0.375, -3.75, 4.375, 0}, {1.875, -8.75, 7.875, 0},
+      {-0.3125, 6.5625, -19.6875, 14.4375}};
+    bg.anyodd = 0;
+    for (int i = 0; i < nl; i++) {
+      const int ell = par->poles[i];
+      for (int q = 0; q < 4; q++) bg.legc[i][q] = LC[ell][q];
+      bg.legodd[i] = ell & 1;
+      bg.anyodd |= ell & 1;
+    }
+  }
   bg.k0 = c->kedge[0]; bg.k1 = c->kedge[nbin]; bg.dk = par->kbin; bg.inv_dk = 1.0 / par->kbin;
 
   const size_t nacc = (size_t) nl * nbin;
@@ -872,26 +931,32 @@ int psb_mesh(psb_context *c, const psb_params *par, const psb_cats *cats) {
   // def_box is evaluated once the stream has drained.  Surveys need the bounds
   // of every catalogue to define the box, so they are made resident first.
   const bool streaming = par->issim && cats->memspace == PSB_MEM_HOST && c->opt_stream;
+  // simulation boxes: box known in advance, bound checks deferred (computed by
+  // the sort's key pass while it reads the catalogue anyway)
+  const bool deferred = par->issim && (streaming || cats->memspace == PSB_MEM_DEVICE);
   const double *dptr[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
   size_t cnt[2][2] = {{0, 0}, {0, 0}};
   double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+  size_t nchunk_total = 0;
   for (int i = 0; i < nc; i++)
     for (int s = 0; s < (par->issim ? 1 : 2); s++) {
       const double *src = s ? cats->rand[i] : cats->data[i];
       const size_t n = s ? cats->nrand[i] : cats->ndata[i];
       cnt[i][s] = n;
       if (n && !src) { set_error("catalogs not read\n"); return -1; }
+      const size_t ch = streaming ? (size_t) std::max<long>(c->opt_stream_chunk, 1 << 16) : DEV_CHUNK;
+      nchunk_total += (n + ch - 1) / ch + 1;
       if (streaming) continue;
       if (cats->memspace == PSB_MEM_DEVICE) dptr[i][s] = src;
       else {
         if (upload(c, src, n, c->part_in[i][s])) return -1;
         dptr[i][s] = c->part_in[i][s].as<double>();
       }
-      if (coordinate_bounds(c, dptr[i][s], n, lo, hi)) return -1;
+      if (!deferred && coordinate_bounds(c, dptr[i][s], n, lo, hi)) return -1;
     }
-  if (streaming) {
+  if (deferred) {
     for (int a = 0; a < 3; a++) { c->bmin[a] = 0; c->bsize[a] = par->bsize[a]; }
-    c->bounds_host.clear();
+    if (bounds_begin(c, nchunk_total)) return -1;
   }
   else {
     for (int a = 0; a < 3; a++) c->bmax[a] = hi[a];
@@ -934,7 +999,7 @@ int psb_mesh(psb_context *c, const psb_params *par, const psb_cats *cats) {
       if (stream_catalog(c, cats->data[i], cnt[i][0], g, par->assign, prec, 1.0, m0, m1)) return -1;
     }
     else {
-      if (assign_catalog(c, dptr[i][0], cnt[i][0], g, par->assign, prec, 1.0, m0, m1)) return -1;
+      if (assign_catalog(c, dptr[i][0], cnt[i][0], g, par->assign, prec, 1.0, m0, m1, deferred)) return -1;
       if (!par->issim &&
           assign_catalog(c, dptr[i][1], cnt[i][1], g, par->assign, prec, -cats->alpha[i], m0, m1))
         return -1;
@@ -951,17 +1016,7 @@ int psb_mesh(psb_context *c, const psb_params *par, const psb_cats *cats) {
       else printf("  Density field generated with %s for the catalog\n", names[par->assign]);
     }
   }
-  if (streaming) {
-    // def_box's checks (src/genr_mesh.c:516-531), after the fact
-    for (size_t q = 0; q + 5 < c->bounds_host.size(); q += 6)
-      for (int a = 0; a < 3; a++) {
-        lo[a] = std::min(lo[a], c->bounds_host[q + a]);
-        hi[a] = std::max(hi[a], c->bounds_host[q + 3 + a]);
-      }
-    for (int a = 0; a < 3; a++) c->bmax[a] = hi[a];
-    double bmin_chk[3], bsize_chk[3];
-    if (define_box(par, lo, hi, bmin_chk, bsize_chk)) return -1;
-  }
+  if (deferred && bounds_finish(c, par)) return -1;
   c->mesh_ready = true;
   return 0;
 }

@@ -47,8 +47,10 @@ int launch_bounds(const double *p, size_t n, double *partials /*[nblk*6]*/,
     int nblk, cudaStream_t st);
 // number of distinct sort keys for this geometry
 size_t row_key_count(const AssignGeom &g);
+int row_keys_blocks(size_t n);
+// partials: optional [row_keys_blocks(n)][6] per-block coordinate bounds
 int launch_row_keys(const double *p, size_t n, const AssignGeom &g,
-    uint32_t *keys, uint32_t *hist, cudaStream_t st);
+    uint32_t *keys, uint32_t *hist, double *partials, cudaStream_t st);
 int launch_row_scatter(const double *p, size_t n, const uint32_t *keys,
     uint32_t *cursor, double *sorted, cudaStream_t st);
 // mesh1 may be null (no interlacing).  precision: 8 or 4.
@@ -84,6 +86,10 @@ struct BinGeom {
   const double *wax[3];         // window factor src/multipole.c:46-100
   const double *pc[3], *ps[3];  // cos/sin(pi n / Ng), interlace phase, :462-484
   const double *k2edge;         // [nbin+1] smallest k^2 landing in each bin (host-bisected)
+  const double *ztab;           // z axis packed per k: {k^2, window, cos, sin, k, 0}
+  double legc[8][4];            // L_ell(x) = [x] (c0 + c1 x^2 + c2 x^4 + c3 x^6) per multipole
+  int legodd[8];
+  int anyodd;
 };
 
 // geometry-only pass: cnt (u64), km (sum of |k| or log k), lcnt[nl][nbin]
