@@ -351,6 +351,15 @@ def main():
         e2e = {"value": world * n / (ms_e2e_step * 1e-3), "unit": "particles/s",
                "ms_per_step": ms_e2e_step, "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": d2h,
                "host_memory": "pinned", "stages_ms": stages_e2e}
+        # the same from PAGEABLE host memory (what the reference's C host hands over:
+        # plain malloc), staged through pinned buffers by the library
+        if world == 1:
+            pageable = host.numpy().copy()
+            cata_pg = Cata(data=[pageable], wdata=[float(n)])
+            ms_pg, _, stages_pg, _, _ = timed(cata_pg, max(1, args.steps // 2), 1)
+            e2e["pageable_ms_per_step"] = ms_pg / max(1, args.steps // 2)
+            e2e["pageable_stages_ms"] = stages_pg
+            del pageable
         del host
 
     # ---- roofline of the dominant hand-written kernel (assignment)

@@ -480,10 +480,9 @@ int stream_catalog(psb_context *c, const double *host, size_t n, const AssignGeo
       PSB_CUDA(cudaEventCreateWithFlags(&c->ev_consumed[s], cudaEventDisableTiming));
     }
   }
-  // whatever ran on the compute stream before (a previous run) must be done
-  // with the chunk buffers
-  PSB_CUDA(cudaEventRecord(c->ev_consumed[0], c->st));
-  PSB_CUDA(cudaEventRecord(c->ev_consumed[1], c->st));
+  // The chunk buffers' last readers recorded ev_consumed[] (previous catalogue or
+  // run; a never-recorded event is a no-op to wait on), so the first upload does
+  // not have to wait for the mesh memsets queued on the compute stream.
   size_t k = 0;
   for (size_t off = 0; off < n; off += CH, k++) {
     const size_t len = std::min(CH, n - off);
