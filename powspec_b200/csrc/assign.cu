@@ -118,8 +118,13 @@ __global__ void __launch_bounds__(256) k_row_keys(const double2 *__restrict__ p,
     int cxl = cx - g.x0;                // plane index inside the owned x-slab
     if (cxl < 0) cxl += g.ng;
     if (cxl >= g.nx) cxl = g.nx - 1;    // not ours (caller's routing error): keep the key in range
-    uint32_t key = ((uint32_t) (cy / g.strip) * (uint32_t) g.nx + (uint32_t) cxl)
-        * (uint32_t) g.strip + (uint32_t) (cy % g.strip);
+    uint32_t key;
+    if (g.xgroup > 0)           // coarse buckets: (strip, group of xgroup planes), unordered inside
+      key = (uint32_t) (cy / g.strip) * (uint32_t) ((g.nx + g.xgroup - 1) / g.xgroup)
+          + (uint32_t) (cxl / g.xgroup);
+    else
+      key = ((uint32_t) (cy / g.strip) * (uint32_t) g.nx + (uint32_t) cxl)
+          * (uint32_t) g.strip + (uint32_t) (cy % g.strip);
     keys[i] = key;
     atomicAdd(hist + key, 1u);
   }
@@ -158,6 +163,7 @@ __global__ void __launch_bounds__(256) k_row_scatter(const double2 *__restrict__
 
 size_t row_key_count(const AssignGeom &g) {
   const size_t nstrip = ((size_t) g.ng + g.strip - 1) / g.strip;
+  if (g.xgroup > 0) return nstrip * (size_t) ((g.nx + g.xgroup - 1) / g.xgroup);
   return nstrip * (size_t) g.nx * (size_t) g.strip;
 }
 

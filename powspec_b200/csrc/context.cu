@@ -142,6 +142,7 @@ struct psb_context {
   long opt_geom_sym = 1;                // fold +-n_x, +-n_y in the mode-counting pass
   long opt_coop = 1;                    // z-coalesced scatter kernel
   long opt_coop_variant = 0;
+  long opt_xgroup = 0;                  // > 0: coarse bucket sort (planes per bucket)
   long opt_strip = 64;                  // rows per strip of the sort order
   long opt_stream = 1;                  // overlap H2D with assignment for host catalogues (sims)
   long opt_stream_chunk = 1 << 24;      // particles per streamed chunk (512 MiB)
@@ -902,6 +903,7 @@ int psb_set_option(psb_context *c, const char *name, long value) {
   if (!strcmp(name, "strip")) { c->opt_strip = value; return 0; }
   if (!strcmp(name, "coop")) { c->opt_coop = value; return 0; }
   if (!strcmp(name, "coop_variant")) { c->opt_coop_variant = value; return 0; }
+  if (!strcmp(name, "xgroup")) { c->opt_xgroup = value; return 0; }
   if (!strcmp(name, "geom_sym")) { c->opt_geom_sym = value; return 0; }
   if (!strcmp(name, "stream")) { c->opt_stream = value; return 0; }
   if (!strcmp(name, "stream_chunk")) { c->opt_stream_chunk = value; return 0; }
@@ -973,6 +975,7 @@ int psb_mesh(psb_context *c, const psb_params *par, const psb_cats *cats) {
   memset(&g, 0, sizeof g);
   g.ng = ng; g.rowlen = rowlen;
   g.strip = (int) std::min<long>(std::max<long>(c->opt_strip, 1), ng);
+  g.xgroup = (int) c->opt_xgroup;
   g.coop = (int) c->opt_coop;
   g.coop_variant = (int) c->opt_coop_variant;
   g.x0 = 0; g.nx = ng; g.xbase = 0; g.nxloc = ng;
@@ -1301,6 +1304,7 @@ static int slab_geom(psb_context *c, const psb_params *par, const psb_slab *sl, 
   memset(&g, 0, sizeof g);
   g.ng = ng; g.rowlen = 2 * (ng / 2 + 1);
   g.strip = (int) std::min<long>(std::max<long>(c->opt_strip, 1), ng);
+  g.xgroup = (int) c->opt_xgroup;
   g.coop = (int) c->opt_coop;
   g.coop_variant = (int) c->opt_coop_variant;
   g.x0 = sl->rank * nx; g.nx = nx;

@@ -32,6 +32,7 @@ struct AssignGeom {
   int ng;               // cells per side
   int rowlen;           // reals per z-row of the (padded, in-place FFT) mesh
   int strip;            // rows per strip of the sort order (row-key layout)
+  int xgroup;           // > 0: coarse sort into (strip, xgroup planes) buckets only
   int coop;             // z-coalesced scatter (NZ lanes per particle)
   int coop_variant;     // launch shape of the z-coalesced kernel (ablation)
   int x0, nx;           // owned x-planes [x0, x0+nx) (single GPU: 0, Ng)
