@@ -27,7 +27,9 @@ namespace psb {
 
 namespace {
 
-enum { MODE_GEOM = 0, MODE_SIM = 1, MODE_SURVEY = 2 };
+__device__ const double g_inv_int[8] = {0.0, 1.0, 0.5, 1.0 / 3.0, 0.25, 0.2, 1.0 / 6.0, 1.0 / 7.0};
+
+enum { MODE_GEOM = 0, MODE_SIM = 1, MODE_SURVEY = 2, MODE_SURVEY_YLM = 3 };
 
 template <typename real> struct C2;
 template <> struct C2<double> { using type = double2; };
@@ -46,6 +48,41 @@ __device__ __forceinline__ double legendre(int ell, double x) {
     case 6: return 14.4375 * x2 * x2 * x2 - 19.6875 * x2 * x2 + 6.5625 * x2 - 0.3125;
     default: return 0.0;
   }
+}
+
+// ---------------------------------------------------------------------------
+// real spherical harmonics (definition math/spherical.h:33-38), by recurrence:
+//   Y_lm = N_lm P_l^|m|(cos t) {cos(m p) | 1 | sin(|m| p)},  P without the
+//   Condon-Shortley phase, N_lm = sqrt((2l+1)/(4 pi) (l-|m|)!/(l+|m|)!) sqrt2^{m!=0}
+// ---------------------------------------------------------------------------
+// split in the part that depends on the azimuth only (constant along a mesh
+// row, where x and y are fixed) and the polar part (varies along the row)
+__device__ __forceinline__ double ylm_azimuth(int m, double cosp, double sinp) {
+  const int am = m < 0 ? -m : m;
+  double cm = 1.0, sm = 0.0;
+  for (int k = 0; k < am; k++) {
+    const double c2 = cm * cosp - sm * sinp;
+    sm = sm * cosp + cm * sinp;
+    cm = c2;
+  }
+  return m > 0 ? cm : (m < 0 ? sm : 1.0);
+}
+
+__device__ __forceinline__ double ylm_polar(int l, int am, double cost, double sint) {
+  double pmm = 1.0;
+  for (int k = 1; k <= am; k++) pmm *= (2 * k - 1) * sint;
+  if (l == am) return pmm;
+  double pm1 = pmm, cur = (2 * am + 1) * cost * pmm;
+  for (int ll = am + 2; ll <= l; ll++) {
+    const double nxt = ((2 * ll - 1) * cost * cur - (ll + am - 1) * pm1) * g_inv_int[ll - am];
+    pm1 = cur; cur = nxt;
+  }
+  return cur;
+}
+
+__device__ __forceinline__ double ylm_real(int l, int m, double nrm, double cost,
+    double sint, double cosp, double sinp) {
+  return nrm * ylm_polar(l, m < 0 ? -m : m, cost, sint) * ylm_azimuth(m, cosp, sinp);
 }
 
 // Bin of a squared wavenumber.  The reference decides it with
@@ -139,6 +176,15 @@ __global__ void __launch_bounds__(256) k_spectrum(BinGeom g, const void *__restr
     const double k2ij = __dadd_rn(__ldg(g.kax2[0] + i), __ldg(g.kax2[1] + j));
     const double wij = __dmul_rn(__ldg(g.wax[0] + i), __ldg(g.wax[1] + j));
     const double muij = __dadd_rn(__dmul_rn(ki, g.los[0]), __dmul_rn(kj, g.los[1]));
+    double yaz = 0.0, kxy2 = 0.0, kxy = 0.0;   // survey l > 0: azimuthal part of Y_lm(k_hat)
+    if (MODE == MODE_SURVEY_YLM) {
+      kxy2 = __dadd_rn(__dmul_rn(ki, ki), __dmul_rn(kj, kj));
+      if (kxy2 != 0.0) {
+        const double rxy = rsqrt(kxy2);
+        kxy = kxy2 * rxy;
+        yaz = g.ylm_nrm * ylm_azimuth(g.m, ki * rxy, kj * rxy);
+      }
+    }
     double pcij = 1.0, psij = 0.0;
     if (INTERLACE) {
       const double ci = __ldg(g.pc[0] + i), si = __ldg(g.ps[0] + i);
@@ -199,6 +245,18 @@ __global__ void __launch_bounds__(256) k_spectrum(BinGeom g, const void *__restr
             p = (a0.x * b0.x + a0.y * b0.y) * alias * mult;
           }
           if (MODE == MODE_SURVEY) v[0] = p;
+          else if (MODE == MODE_SURVEY_YLM) {
+            // Re(Fk0 conj Fka_m) Y_lm(k_hat): by linearity this sums to the
+            // reference's Re(Fk0 conj Fkl), Fkl = sum_m Fka_m Y_lm(k_hat)
+            // (src/mp_template.c:101-137), without the Fkl field.  k_xy = 0 or
+            // |k| = 0 enter unweighted (:121-124).
+            double sh = 1.0;
+            if (kxy2 != 0.0 && k2 != 0.0) {
+              const double kz = __ldg(g.kax[2] + k);
+              sh = yaz * ylm_polar(g.ell, g.m < 0 ? -g.m : g.m, kz * rk, kxy * rk);
+            }
+            v[0] = p * sh;
+          }
           else {
             // mu = k.los / |k|  (src/multipole.c:812-813)
             const double mu = __dadd_rn(muij, __dmul_rn(__ldg(g.kax[2] + k), g.los[2])) * rk;
@@ -347,6 +405,8 @@ template <typename real>
 static int launch_bin_t(const BinGeom &g, const void *Fa0, const void *Fa1, const void *Fb0,
     const void *Fb1, double *pl, double *scratch, size_t sb, cudaStream_t st) {
   const bool il = (Fa1 != nullptr);
+  if (!g.issim && g.ell > 0)
+    return run_spectrum<real, 1, MODE_SURVEY_YLM, false>(g, Fa0, nullptr, Fb0, nullptr, pl, scratch, sb, st);
   if (!g.issim) {
     return il ? run_spectrum<real, 1, MODE_SURVEY, true>(g, Fa0, Fa1, Fb0, Fb1, pl, scratch, sb, st)
               : run_spectrum<real, 1, MODE_SURVEY, false>(g, Fa0, Fa1, Fb0, Fb1, pl, scratch, sb, st);
@@ -407,35 +467,7 @@ int launch_combine(const BinGeom &g, int precision, void *F0, const void *F1,
   return 0;
 }
 
-// ---------------------------------------------------------------------------
-// real spherical harmonics (definition math/spherical.h:33-38), by recurrence:
-//   Y_lm = N_lm P_l^|m|(cos t) {cos(m p) | 1 | sin(|m| p)},  P without the
-//   Condon-Shortley phase, N_lm = sqrt((2l+1)/(4 pi) (l-|m|)!/(l+|m|)!) sqrt2^{m!=0}
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ double ylm_real(int l, int m, double nrm, double cost,
-    double sint, double cosp, double sinp) {
-  const int am = m < 0 ? -m : m;
-  double cm = 1.0, sm = 0.0;
-  for (int k = 0; k < am; k++) {
-    const double c2 = cm * cosp - sm * sinp;
-    sm = sm * cosp + cm * sinp;
-    cm = c2;
-  }
-  double pmm = 1.0;
-  for (int k = 1; k <= am; k++) pmm *= (2 * k - 1) * sint;
-  double plm = pmm;
-  if (l > am) {
-    double pm1 = pmm, cur = (2 * am + 1) * cost * pmm;
-    for (int ll = am + 2; ll <= l; ll++) {
-      const double nxt = ((2 * ll - 1) * cost * cur - (ll + am - 1) * pm1) / (ll - am);
-      pm1 = cur; cur = nxt;
-    }
-    plm = cur;
-  }
-  return nrm * plm * (m > 0 ? cm : (m < 0 ? sm : 1.0));
-}
-
-static double ylm_norm(int l, int m) {
+double ylm_norm(int l, int m) {
   const int am = m < 0 ? -m : m;
   double ratio = 1.0;
   for (int k = l - am + 1; k <= l + am; k++) ratio /= k;
@@ -455,13 +487,17 @@ __global__ void __launch_bounds__(256) k_ylm_weight_r(YlmGeom g, double nrm,
     const double rj = (j + g.smin[1]) * g.bsize[1];
     const double r2 = ri * ri + rj * rj;
     const double rxy = sqrt(r2);
+    // azimuth (cos phi = ri / rxy, sin phi = rj / rxy) is constant along the row
+    // (a row through the origin has no azimuth; its polar factor sin^|m| is 0 for m != 0)
+    const double az = nrm * (rxy > 0.0 ? ylm_azimuth(g.m, ri / rxy, rj / rxy) : 1.0);
+    const int am = g.m < 0 ? -g.m : g.m;
     const real *src = Fr + row * g.rowlen;
     real *dst = out + row * g.rowlen;
     for (int k = threadIdx.x; k < g.ng; k += blockDim.x) {
       if (row == 0) { dst[k] = src[k]; continue; }      // quirk Q5 (:75-78)
       const double rk = (k + g.smin[2]) * g.bsize[2];
-      const double r3 = sqrt(r2 + rk * rk);
-      const double y = ylm_real(g.ell, g.m, nrm, rk / r3, rxy / r3, ri / rxy, rj / rxy);
+      const double ir3 = rsqrt(r2 + rk * rk);
+      const double y = az * ylm_polar(g.ell, am, rk * ir3, rxy * ir3);
       dst[k] = (real) ((double) src[k] * y);
     }
   }

@@ -142,6 +142,7 @@ struct psb_context {
   long opt_geom_sym = 1;                // fold +-n_x, +-n_y in the mode-counting pass
   long opt_coop = 1;                    // z-coalesced scatter kernel
   long opt_coop_variant = 0;
+  long opt_survey_direct = 1;           // survey l > 0: bin Fk0 x Fka_m directly (no Fkl field)
   long opt_xgroup = 0;                  // > 0: coarse bucket sort (planes per bucket)
   long opt_strip = 64;                  // rows per strip of the sort order
   long opt_stream = 1;                  // overlap H2D with assignment for host catalogues (sims)
@@ -904,6 +905,7 @@ int psb_set_option(psb_context *c, const char *name, long value) {
   if (!strcmp(name, "coop")) { c->opt_coop = value; return 0; }
   if (!strcmp(name, "coop_variant")) { c->opt_coop_variant = value; return 0; }
   if (!strcmp(name, "xgroup")) { c->opt_xgroup = value; return 0; }
+  if (!strcmp(name, "survey_direct")) { c->opt_survey_direct = value; return 0; }
   if (!strcmp(name, "geom_sym")) { c->opt_geom_sym = value; return 0; }
   if (!strcmp(name, "stream")) { c->opt_stream = value; return 0; }
   if (!strcmp(name, "stream_chunk")) { c->opt_stream_chunk = value; return 0; }
@@ -1171,9 +1173,12 @@ psb_result *psb_power(psb_context *c, const psb_params *par) {
     for (int n = 1; n < nl; n++) {
       const int ell = par->poles[n];
       if (c->fka.reserve(mesh_bytes)) return fail();
+      const bool direct = c->opt_survey_direct != 0;
       for (int i = 0; i < nc; i++) {
-        if (c->fkl[i].reserve(mesh_bytes)) return fail();
-        if (hard(cudaMemsetAsync(c->fkl[i].p, 0, mesh_bytes, c->st))) return fail();
+        if (!direct) {
+          if (c->fkl[i].reserve(mesh_bytes)) return fail();
+          if (hard(cudaMemsetAsync(c->fkl[i].p, 0, mesh_bytes, c->st))) return fail();
+        }
         YlmGeom yg;
         yg.ng = ng; yg.ngk = ngk; yg.rowlen = 2 * ngk; yg.ell = ell;
         for (int a = 0; a < 3; a++) {
@@ -1188,15 +1193,38 @@ psb_result *psb_power(psb_context *c, const psb_params *par) {
             c->launches++;
           }
           if (fft_forward(c, c->fka.p)) return fail();
-          StageScope sc(c, PSB_T_YLM, c->st);
-          if (launch_ylm_accum_k(yg, bg, prec, c->fka.p, c->fkl[i].p, c->st)) return fail();
-          c->launches++;
+          if (!direct) {
+            StageScope sc(c, PSB_T_YLM, c->st);
+            if (launch_ylm_accum_k(yg, bg, prec, c->fka.p, c->fkl[i].p, c->st)) return fail();
+            c->launches++;
+            continue;
+          }
+          // Direct binning of Re(Fk0 conj Fka_m) Y_lm(k_hat): the sum over m is
+          // the reference's Re(Fk0 conj Fkl) by linearity, without the Fkl field
+          // and its read-modify-write pass per m.
+          BinGeom bm = bg;
+          bm.ell = ell; bm.m = m; bm.ylm_nrm = ylm_norm(ell, m);
+          StageScope sc(c, PSB_T_BIN, c->st);
+          if (par->isauto[i]) {
+            if (launch_bin(bm, prec, Fk0[i], nullptr, c->fka.p, nullptr, d_pl[i] + (size_t) n * nbin,
+                  scratch_bin, sb, c->st))
+              return fail();
+            c->launches += 2;
+          }
+          if (par->iscross && nc == 2) {
+            // (Fk0[0], Fkl[1]) + (Fk0[1], Fkl[0]), src/multipole.c:1134-1135
+            if (launch_bin(bm, prec, Fk0[1 - i], nullptr, c->fka.p, nullptr, d_xpl + (size_t) n * nbin,
+                  scratch_bin, sb, c->st))
+              return fail();
+            c->launches += 2;
+          }
         }
         if (par->verbose) {
           if (nc != 2) printf("  Done with computing %d FFTs for l = %d\n", 2 * ell + 1, ell);
           else printf("  Done with computing %d FFTs for l = %d with catalog %d\n", 2 * ell + 1, ell, i + 1);
         }
       }
+      if (direct) continue;
       StageScope sc(c, PSB_T_BIN, c->st);
       for (int i = 0; i < nc; i++) {
         if (!par->isauto[i]) continue;

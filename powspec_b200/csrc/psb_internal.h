@@ -91,6 +91,8 @@ struct BinGeom {
   double legc[8][4];            // L_ell(x) = [x] (c0 + c1 x^2 + c2 x^4 + c3 x^6) per multipole
   int legodd[8];
   int anyodd;
+  int ell, m;                   // survey l > 0: weight the product by Y_lm(k_hat)
+  double ylm_nrm;
 };
 
 // geometry-only pass: cnt (u64), km (sum of |k| or log k), lcnt[nl][nbin]
@@ -118,6 +120,7 @@ int launch_ylm_weight_r(const YlmGeom &g, int precision, const void *Fr, void *o
 int launch_ylm_accum_k(const YlmGeom &g, const BinGeom &bg, int precision,
     const void *Fka, void *Fkl, cudaStream_t st);
 int launch_scale(void *mesh, size_t n, double factor, int precision, cudaStream_t st);
+double ylm_norm(int l, int m);
 
 // generate.cu
 int launch_generate(double *out, size_t n, double boxsize, int kind, uint64_t seed,
