@@ -15,6 +15,8 @@
 // Runtime knobs the reference fixes at compile time:
 //   POWSPEC_B200_PRECISION = 8 | 4   (the reference's -DSINGLE_PREC, Makefile:14)
 //   POWSPEC_B200_DEVICE    = CUDA device ordinal (default 0)
+//   POWSPEC_B200_TIMING    = path: write a JSON line with the device stage timings
+//                            (CUDA events) of the run; never touches the output file
 
 #include "../../include/powspec_b200.h"
 #include "../../include/powspec_refabi.h"
@@ -188,6 +190,18 @@ psb_ref_PK *powspec(const psb_ref_CONF *conf, const psb_ref_CATA *cat, psb_ref_M
   }
   free(flat);
   psb_result_free(res);
+  if (const char *tpath = getenv("POWSPEC_B200_TIMING")) {
+    static const char *names[] = {"h2d", "bounds", "sort", "memset", "assign", "fft", "geom", "bin", "ylm"};
+    double ms[PSB_T_COUNT];
+    if (*tpath && psb_timings(g_ctx, ms, PSB_T_COUNT) > 0) {
+      if (FILE *f = fopen(tpath, "a")) {
+        fprintf(f, "{\"grid\": %d, \"launches\": %ld, \"stages_ms\": {", conf->gsize, psb_launch_count(g_ctx));
+        for (int i = 0; i < 9; i++) fprintf(f, "%s\"%s\": %.4f", i ? ", " : "", names[i], ms[i]);
+        fprintf(f, "}}\n");
+        fclose(f);
+      }
+    }
+  }
   if (!ok) {
     P_ERR("failed to initialise the power spectra\n");
     powspec_destroy(pk);

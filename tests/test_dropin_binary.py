@@ -73,8 +73,15 @@ OVERWRITE = 1
 VERBOSE = F
 """)
     _run(REF_BIN, "sim.conf", ["-a", "[ref_a.txt,ref_b.txt]", "-x", "ref_x.txt"], tmp_path, 4)
-    out = _run(OUR_BIN, "sim.conf", ["-a", "[our_a.txt,our_b.txt]", "-x", "our_x.txt"], tmp_path, 4)
+    os.environ["POWSPEC_B200_TIMING"] = str(tmp_path / "timing.jsonl")
+    try:
+        out = _run(OUR_BIN, "sim.conf", ["-a", "[our_a.txt,our_b.txt]", "-x", "our_x.txt"], tmp_path, 4)
+    finally:
+        del os.environ["POWSPEC_B200_TIMING"]
     assert "Generating meshes for FFT" in out and "Evaluating power spectra" in out
+    import json
+    rec = json.loads((tmp_path / "timing.jsonl").read_text().splitlines()[-1])
+    assert rec["grid"] == 32 and rec["launches"] > 0 and rec["stages_ms"]["assign"] > 0
     for t in ("a", "b", "x"):
         _compare(tmp_path / f"ref_{t}.txt", tmp_path / f"our_{t}.txt")
 
