@@ -232,8 +232,10 @@ def build_ref(reference="/root/reference") -> str | None:
     """Build oracle/_ref from the reference sources where they lie; a no-op
     (returning the prebuilt library, if any) when the tree is absent."""
     if os.path.isdir(os.path.join(reference, "src")):
-        subprocess.check_call(["make", "-C", HERE, "ref", f"REF={reference}"],
-                              stdout=subprocess.DEVNULL)
+        # `dropin` also links the reference's unchanged host against the product
+        # library (oracle/_ref/POWSPEC_b200) for tests/test_dropin_binary.py
+        subprocess.check_call(["make", "-C", HERE, "ref", "dropin", f"REF={reference}"],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     return REF_LIB if have_ref() else None
 
 
