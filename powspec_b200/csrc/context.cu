@@ -122,7 +122,11 @@ struct psb_context {
   DevBuf fkl[2], fka, fk0copy[2];
 
   // FFT
-  cufftHandle plan_fwd = 0, plan_inv = 0;
+  cufftHandle plan_fwd = 0, plan_inv = 0, plan_z = 0;
+  bool have_z = false;
+  bool own_fft = false;                 // y/x passes by k_fft1024_strided (double, Ng = 1024)
+  double fft_k2max = 0;                 // last bin edge in k^2 (tile skipping of the x pass)
+  bool fft_skip = false;
   int plan_ng = 0, plan_prec = 0;
   bool have_fwd = false, have_inv = false;
   DevBuf fftwork;
@@ -143,6 +147,8 @@ struct psb_context {
   long opt_coop = 1;                    // z-coalesced scatter kernel
   long opt_coop_variant = 0;
   long opt_survey_direct = 1;           // survey l > 0: bin Fk0 x Fka_m directly (no Fkl field)
+  long opt_fft_variant = 2;             // 8 columns per tile, 512 threads, one block per SM
+  long opt_own_fft = 1;                 // hand-written strided FFT passes where available
   long opt_xgroup = 0;                  // > 0: coarse bucket sort (planes per bucket)
   long opt_strip = 64;                  // rows per strip of the sort order
   long opt_stream = 1;                  // overlap H2D with assignment for host catalogues (sims)
@@ -565,7 +571,8 @@ int ensure_plans(psb_context *c, int ng, int precision, bool need_inv) {
   if (c->plan_ng != ng || c->plan_prec != precision) {
     if (c->have_fwd) cufftDestroy(c->plan_fwd);
     if (c->have_inv) cufftDestroy(c->plan_inv);
-    c->have_fwd = c->have_inv = false;
+    if (c->have_z) cufftDestroy(c->plan_z);
+    c->have_fwd = c->have_inv = c->have_z = false;
     c->plan_ng = ng; c->plan_prec = precision;
   }
   const int ngk = ng / 2 + 1;
@@ -591,8 +598,22 @@ int ensure_plans(psb_context *c, int ng, int precision, bool need_inv) {
     c->have_inv = true;
   }
   else if (c->have_inv) PSB_CUFFT(cufftGetSize(c->plan_inv, &ws_i));
-  const size_t ws = std::max(ws_f, ws_i);
+  // the hand-written strided passes need only a batched 1-D r2c along z from cuFFT
+  c->own_fft = c->opt_own_fft && precision == 8 && ng == 1024;
+  size_t ws_z = 0;
+  if (c->own_fft && !c->have_z) {
+    long long n1[1] = {ng}, re1[1] = {2LL * ngk}, ce1[1] = {ngk};
+    PSB_CUFFT(cufftCreate(&c->plan_z));
+    PSB_CUFFT(cufftSetAutoAllocation(c->plan_z, 0));
+    PSB_CUFFT(cufftMakePlanMany64(c->plan_z, 1, n1, re1, 1, 2LL * ngk, ce1, 1, ngk, CUFFT_D2Z,
+        (long long) ng * ng, &ws_z));
+    PSB_CUFFT(cufftSetStream(c->plan_z, c->st));
+    c->have_z = true;
+  }
+  else if (c->have_z) PSB_CUFFT(cufftGetSize(c->plan_z, &ws_z));
+  const size_t ws = std::max(std::max(ws_f, ws_i), ws_z);
   if (c->fftwork.reserve(ws ? ws : 256)) return -1;
+  if (c->have_z) PSB_CUFFT(cufftSetWorkArea(c->plan_z, c->fftwork.p));
   PSB_CUFFT(cufftSetWorkArea(c->plan_fwd, c->fftwork.p));
   if (c->have_inv) PSB_CUFFT(cufftSetWorkArea(c->plan_inv, c->fftwork.p));
   return 0;
@@ -601,6 +622,21 @@ int ensure_plans(psb_context *c, int ng, int precision, bool need_inv) {
 int fft_forward(psb_context *c, void *mesh) {
   StageScope sc(c, PSB_T_FFT, c->st);
   c->launches++;
+  if (c->own_fft) {
+    // z: cuFFT batched 1-D r2c; y, x: hand-written strided passes (fft1024.cu).
+    // The x pass skips the columns beyond the last bin edge when only the
+    // binning reads the result (simulation boxes).
+    PSB_CUFFT(cufftExecD2Z(c->plan_z, (cufftDoubleReal *) mesh, (cufftDoubleComplex *) mesh));
+    const int ngk = c->plan_ng / 2 + 1;
+    const int fv = (int) c->opt_fft_variant;
+    if (launch_fft1024_strided(mesh, ngk, 1, nullptr, nullptr, 0.0, fv, c->st)) return -1;
+    const bool skip = c->fft_skip && c->bins_ready;
+    if (launch_fft1024_strided(mesh, ngk, 0, skip ? c->bg.kax2[1] : nullptr,
+          skip ? c->bg.kax2[2] : nullptr, c->fft_k2max, fv, c->st))
+      return -1;
+    c->launches += 2;
+    return 0;
+  }
   if (c->plan_prec == 8)
     PSB_CUFFT(cufftExecD2Z(c->plan_fwd, (cufftDoubleReal *) mesh, (cufftDoubleComplex *) mesh));
   else
@@ -875,6 +911,7 @@ void psb_destroy(psb_context *c) {
   cudaDeviceSynchronize();
   if (c->have_fwd) cufftDestroy(c->plan_fwd);
   if (c->have_inv) cufftDestroy(c->plan_inv);
+  if (c->have_z) cufftDestroy(c->plan_z);
   if (c->slab_have) { cufftDestroy(c->slab_yz); cufftDestroy(c->slab_x); }
   for (int i = 0; i < 2; i++) {
     for (int j = 0; j < 2; j++) { c->part_in[i][j].release(); c->mesh[i][j].release(); }
@@ -905,6 +942,8 @@ int psb_set_option(psb_context *c, const char *name, long value) {
   if (!strcmp(name, "coop")) { c->opt_coop = value; return 0; }
   if (!strcmp(name, "coop_variant")) { c->opt_coop_variant = value; return 0; }
   if (!strcmp(name, "xgroup")) { c->opt_xgroup = value; return 0; }
+  if (!strcmp(name, "own_fft")) { c->opt_own_fft = value; return 0; }
+  if (!strcmp(name, "fft_variant")) { c->opt_fft_variant = value; return 0; }
   if (!strcmp(name, "survey_direct")) { c->opt_survey_direct = value; return 0; }
   if (!strcmp(name, "geom_sym")) { c->opt_geom_sym = value; return 0; }
   if (!strcmp(name, "stream")) { c->opt_stream = value; return 0; }
@@ -1088,6 +1127,8 @@ psb_result *psb_power(psb_context *c, const psb_params *par) {
   double *scratch_bin = reinterpret_cast<double *>(c->binscratch.as<char>() + sb);
   // the bins are zeroed and the tables uploaded on the side stream
   if (hard(cudaStreamWaitEvent(c->st, c->ev_geom, 0))) return fail();
+  c->fft_skip = issim;          // only the binning reads delta(k) of a simulation box
+  c->fft_k2max = c->host_tables[15 * (size_t) ng + nbin];
 
   // ---- dens_k0, src/multipole.c:435-505
   if (ensure_plans(c, ng, prec, need_ell && il)) return fail();

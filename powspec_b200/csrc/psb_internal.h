@@ -122,6 +122,11 @@ int launch_ylm_accum_k(const YlmGeom &g, const BinGeom &bg, int precision,
 int launch_scale(void *mesh, size_t n, double factor, int precision, cudaStream_t st);
 double ylm_norm(int l, int m);
 
+// fft1024.cu: in-place forward 1024-point pass along y (axis 1) or x (axis 0) of a
+// (1024, 1024, ngk) complex double array; optional tile skipping for the x pass
+int launch_fft1024_strided(void *data, int ngk, int axis, const double *k2a, const double *k2b,
+    double k2max, int variant, cudaStream_t st);
+
 // generate.cu
 int launch_generate(double *out, size_t n, double boxsize, int kind, uint64_t seed,
     cudaStream_t st);
