@@ -137,10 +137,11 @@ int psb_copy_mesh(psb_context *ctx, int cat, int field, void *dst);
 int psb_mesh_box(const psb_context *ctx, double bmin[3], double bsize[3], double bmax[3]);
 
 /* Device timings of the last run, in milliseconds, measured with CUDA events on
- * the context's stream.  Index with PSB_T_*. */
+ * the context's stream.  Index with PSB_T_*.  PSB_T_FFT covers the whole transforms;
+ * PSB_T_FFT_STRIDED is the part of it spent in the hand-written strided passes. */
 enum {
   PSB_T_H2D = 0, PSB_T_BOUNDS, PSB_T_SORT, PSB_T_MEMSET, PSB_T_ASSIGN,
-  PSB_T_FFT, PSB_T_GEOM, PSB_T_BIN, PSB_T_YLM, PSB_T_TOTAL, PSB_T_COUNT
+  PSB_T_FFT, PSB_T_GEOM, PSB_T_BIN, PSB_T_YLM, PSB_T_FFT_STRIDED, PSB_T_TOTAL, PSB_T_COUNT
 };
 int psb_timings(const psb_context *ctx, double *ms, int n);
 /* number of kernel launches (ours + cuFFT calls counted as 1) of the last run */

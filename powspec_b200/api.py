@@ -33,9 +33,10 @@ powspec_assign_names = ["NGP", "CIC", "TSC", "PCS"]
 POWSPEC_ERR_MESH = -13      # src/define.h:122
 POWSPEC_ERR_PK = -14        # src/define.h:123
 
-(T_H2D, T_BOUNDS, T_SORT, T_MEMSET, T_ASSIGN, T_FFT, T_GEOM, T_BIN, T_YLM, T_TOTAL,
- T_COUNT) = range(11)
-TIMING_NAMES = ["h2d", "bounds", "sort", "memset", "assign", "fft", "geom", "bin", "ylm", "total"]
+(T_H2D, T_BOUNDS, T_SORT, T_MEMSET, T_ASSIGN, T_FFT, T_GEOM, T_BIN, T_YLM, T_FFT_STRIDED,
+ T_TOTAL, T_COUNT) = range(12)
+TIMING_NAMES = ["h2d", "bounds", "sort", "memset", "assign", "fft", "geom", "bin", "ylm",
+                "fft_strided", "total"]
 
 (GET_K, GET_KEDGE, GET_KM, GET_CNT, GET_LCNT, GET_PL, GET_XPL, GET_SHOT, GET_NORM,
  GET_BMIN, GET_BSIZE, GET_BMAX) = range(12)

@@ -629,6 +629,7 @@ int fft_forward(psb_context *c, void *mesh) {
     PSB_CUFFT(cufftExecD2Z(c->plan_z, (cufftDoubleReal *) mesh, (cufftDoubleComplex *) mesh));
     const int ngk = c->plan_ng / 2 + 1;
     const int fv = (int) c->opt_fft_variant;
+    StageScope own(c, PSB_T_FFT_STRIDED, c->st);
     if (launch_fft1024_strided(mesh, ngk, 1, nullptr, nullptr, 0.0, fv, c->st)) return -1;
     const bool skip = c->fft_skip && c->bins_ready;
     if (launch_fft1024_strided(mesh, ngk, 0, skip ? c->bg.kax2[1] : nullptr,
@@ -1307,7 +1308,7 @@ psb_result *psb_power(psb_context *c, const psb_params *par) {
   c->mesh_ready = false;        // the FFTs ran in place: the meshes are consumed
   c->bins_ready = false;
   c->ms[PSB_T_TOTAL] = 0;
-  for (int s = 0; s < PSB_T_TOTAL; s++) c->ms[PSB_T_TOTAL] += c->ms[s];
+  for (int s = 0; s < PSB_T_TOTAL; s++) if (s != PSB_T_FFT_STRIDED) c->ms[PSB_T_TOTAL] += c->ms[s];
   return res;
 }
 

@@ -191,12 +191,13 @@ psb_ref_PK *powspec(const psb_ref_CONF *conf, const psb_ref_CATA *cat, psb_ref_M
   free(flat);
   psb_result_free(res);
   if (const char *tpath = getenv("POWSPEC_B200_TIMING")) {
-    static const char *names[] = {"h2d", "bounds", "sort", "memset", "assign", "fft", "geom", "bin", "ylm"};
+    static const char *names[] = {"h2d", "bounds", "sort", "memset", "assign", "fft", "geom", "bin", "ylm",
+      "fft_strided"};
     double ms[PSB_T_COUNT];
     if (*tpath && psb_timings(g_ctx, ms, PSB_T_COUNT) > 0) {
       if (FILE *f = fopen(tpath, "a")) {
         fprintf(f, "{\"grid\": %d, \"launches\": %ld, \"stages_ms\": {", conf->gsize, psb_launch_count(g_ctx));
-        for (int i = 0; i < 9; i++) fprintf(f, "%s\"%s\": %.4f", i ? ", " : "", names[i], ms[i]);
+        for (int i = 0; i < 10; i++) fprintf(f, "%s\"%s\": %.4f", i ? ", " : "", names[i], ms[i]);
         fprintf(f, "}}\n");
         fclose(f);
       }
