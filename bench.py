@@ -389,15 +389,16 @@ def main():
                     "fft": {"ms": stages.get("fft", 0.0), "algorithmic_bytes": b_fft,
                             "GBps": b_fft / max(stages.get("fft", 1e-9), 1e-9) / 1e6,
                             "frac": b_fft / max(stages.get("fft", 1e-9), 1e-9) / 1e6 / peak,
-                            "note": "z pass: cuFFT batched 1-D D2Z; y and x passes: k_fft1024_strided "
-                                    "(hand-written) when Ng = 1024 and double, else cuFFT"},
-                    "fft_strided": {"kernel": "k_fft1024_strided<8,1>", "launches": 2 * F,
-                                    "ms": stages.get("fft_strided", 0.0),
-                                    "algorithmic_bytes_per_launch": ncmplx * 2 * s_real * 2,
-                                    "GBps": 2 * F * ncmplx * 4 * s_real / max(stages.get("fft_strided", 1e-9), 1e-9) / 1e6,
-                                    "frac": 2 * F * ncmplx * 4 * s_real / max(stages.get("fft_strided", 1e-9), 1e-9) / 1e6 / peak,
-                                    "note": "each pass reads and writes every complex cell once; the x pass "
-                                            "skips the columns beyond the last k edge (counted as moved here)"},
+                            "note": "z pass: cuFFT batched 1-D r2c, y and x passes: k_fft_strided "
+                                    "(hand-written; Ng in 512/1024/1536/2048), z + y run group by group "
+                                    "over planes that fit the L2 (option fft_l2_mb); else cuFFT 3-D"},
+                    "fft_x_pass": {"kernel": "k_fft_strided (x pass)", "launches": F,
+                                   "ms": stages.get("fft_strided", 0.0),
+                                   "algorithmic_bytes_per_launch": ncmplx * 2 * s_real * 2,
+                                   "GBps": F * ncmplx * 4 * s_real / max(stages.get("fft_strided", 1e-9), 1e-9) / 1e6,
+                                   "frac": F * ncmplx * 4 * s_real / max(stages.get("fft_strided", 1e-9), 1e-9) / 1e6 / peak,
+                                   "note": "reads and writes every complex cell once; skips the columns "
+                                           "beyond the last k edge (counted as moved here)"},
                     "bin": {"ms": stages.get("bin", 0.0), "algorithmic_bytes": b_bin,
                             "GBps": b_bin / max(stages.get("bin", 1e-9), 1e-9) / 1e6,
                             "frac": b_bin / max(stages.get("bin", 1e-9), 1e-9) / 1e6 / peak,

@@ -182,6 +182,16 @@ int psb_slab_bin(psb_context *ctx, const psb_params *par, const psb_slab *slab,
 psb_result *psb_slab_finish(psb_context *ctx, const psb_params *par, const double *pl0,
     const double *pl1, const double *xpl, const double wdata[2]);
 
+/* One in-place forward pass (sign -1, unnormalised: the convention of the FFTW
+ * r2c plan of src/genr_mesh.c:738-743 along one axis) of the hand-written
+ * strided FFT over caller-owned device memory: complex double (precision 8) or
+ * float (4), rows of ngk elements; axis 1: along y of (outer_n, ng, ngk);
+ * axis 0: along x of (ng, outer_n, ngk); axis 2: real-to-complex along z of
+ * outer_n contiguous rows of 2 ngk reals (ng used, ngk = ng/2 + 1), in place.
+ * ng in {512, 1024, 1536, 2048}. */
+int psb_fft_axis(psb_context *ctx, void *data_dev, int precision, int ng, int ngk, int axis,
+    int outer_n);
+
 /* Device-side synthetic catalogue generator for benchmarks:
  * fills n x {x,y,z,w} on the device; kind 0 = uniform in [0,L)^3, 1 = clustered.
  * Returns a device pointer to be released with psb_device_free. */

@@ -114,6 +114,7 @@ def load_library():
     L.psb_device_free.argtypes = [C.c_void_p, C.c_void_p]
     L.psb_generate_into.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_int, C.c_uint64, C.c_uint64]
     L.psb_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.psb_fft_axis.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     _lib = L
     return L
 
@@ -363,6 +364,25 @@ class Context:
                                     int(seed), int(first_index)):
             raise _err(self.L, "psb_generate_into")
         return tensor
+
+    def fft_axis(self, tensor, axis: int):
+        """In-place forward FFT along axis 0 or 1 of a 3-D complex CUDA tensor
+        (hand-written strided pass; the other two axes are (outer, k))."""
+        prec = 8 if tensor.element_size() == 16 else 4
+        ng = tensor.shape[axis]
+        if self.L.psb_fft_axis(self.h, tensor.data_ptr(), prec, ng, tensor.shape[2], axis,
+                               tensor.shape[1 - axis]):
+            raise _err(self.L, "psb_fft_axis")
+        return tensor
+
+    def fft_rows(self, tensor, ng: int):
+        """In-place r2c FFT of the rows of a real (nrows, 2 (ng/2+1)) CUDA tensor
+        (hand-written z pass); returns the complex (nrows, ng/2+1) view."""
+        import torch
+        prec = tensor.element_size()
+        if self.L.psb_fft_axis(self.h, tensor.data_ptr(), prec, ng, ng // 2 + 1, 2, tensor.shape[0]):
+            raise _err(self.L, "psb_fft_axis")
+        return torch.view_as_complex(tensor.view(tensor.shape[0], ng // 2 + 1, 2))
 
     def free_catalog(self, cat):
         self.L.psb_device_free(self.h, cat[0])

@@ -3,7 +3,7 @@
     python -m powspec_b200.build [--force]
 
 The library is the product: hand-written CUDA kernels (csrc/assign.cu,
-csrc/binning.cu, csrc/generate.cu), the host orchestration + C ABI
+csrc/binning.cu, csrc/fft_strided.cu, csrc/generate.cu), the host orchestration + C ABI
 (csrc/context.cu) and the reference-ABI seam (csrc/refabi.cpp).  It links
 cuFFT dynamically and the CUDA runtime statically.  No GPU is needed to build.
 """
@@ -21,7 +21,7 @@ ROOT = os.path.dirname(HERE)
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libpowspec_b200.so")
 
-SOURCES = ["assign.cu", "binning.cu", "fft1024.cu", "generate.cu", "context.cu", "refabi.cpp"]
+SOURCES = ["assign.cu", "binning.cu", "fft_strided.cu", "generate.cu", "context.cu", "refabi.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -105,6 +105,9 @@ struct psb_context {
   cudaStream_t st = nullptr;            // compute
   cudaStream_t st_geom = nullptr;       // data-independent mode counting
   cudaEvent_t ev_geom = nullptr;
+  cudaStream_t st_aux = nullptr;        // mesh memsets, overlapped with the particle sort
+  cudaEvent_t ev_aux_go = nullptr, ev_aux_done = nullptr, ev_memset[2] = {nullptr, nullptr};
+  cudaEvent_t memset_pending = nullptr; // the scatter must wait for this memset first
 
   // particles
   DevBuf part_in[2][2];                 // [cat][data|rand] staged copies of host arrays
@@ -122,19 +125,18 @@ struct psb_context {
   DevBuf fkl[2], fka, fk0copy[2];
 
   // FFT
-  cufftHandle plan_fwd = 0, plan_inv = 0, plan_z = 0;
-  bool have_z = false;
-  bool own_fft = false;                 // y/x passes by k_fft1024_strided (double, Ng = 1024)
+  cufftHandle plan_fwd = 0, plan_inv = 0, plan_z = 0, plan_z2 = 0;
+  bool have_z = false, have_z2 = false;
+  bool own_fft = false;                 // y/x passes by k_fft_strided (fft_strided.cu)
   double fft_k2max = 0;                 // last bin edge in k^2 (tile skipping of the x pass)
-  bool fft_skip = false;
-  int plan_ng = 0, plan_prec = 0;
+  int plan_ng = 0, plan_prec = 0, plan_zp = 0;
   bool have_fwd = false, have_inv = false;
   DevBuf fftwork;
 
   // slab-decomposed FFT plans
   cufftHandle slab_yz = 0, slab_x = 0;
-  int slab_ng = 0, slab_nx = 0, slab_prec = 0;
-  bool slab_have = false;
+  int slab_ng = 0, slab_nx = 0, slab_prec = 0, slab_zp = 1;
+  bool slab_have = false, slab_own = false;
 
   // tables and bins
   DevBuf tables, binscratch, bins;
@@ -147,7 +149,11 @@ struct psb_context {
   long opt_coop = 1;                    // z-coalesced scatter kernel
   long opt_coop_variant = 0;
   long opt_survey_direct = 1;           // survey l > 0: bin Fk0 x Fka_m directly (no Fkl field)
-  long opt_fft_variant = 2;             // 8 columns per tile, 512 threads, one block per SM
+  long opt_fft_skip = 1;                // x pass skips the columns beyond the last bin edge
+  long opt_fft_l2_mb = 0;               // L2 budget of a z + y plane group (0: whole mesh at once)
+  long opt_fft_streams = 1;             // 2: alternate the plane groups between two streams
+  long opt_fft_own_z = -1;              // hand-written r2c z pass: 1 / 0 (cuFFT batched 1-D) / -1 auto
+  long opt_memset_overlap = 0;          // mesh memsets on a side stream, under the particle sort
   long opt_own_fft = 1;                 // hand-written strided FFT passes where available
   long opt_xgroup = 0;                  // > 0: coarse bucket sort (planes per bucket)
   long opt_strip = 64;                  // rows per strip of the sort order
@@ -340,6 +346,7 @@ int sort_assign_chunk(psb_context *c, const double *src, size_t len, const Assig
     }
   }
   if (!do_sort) {
+    if (c->memset_pending) { PSB_CUDA(cudaStreamWaitEvent(c->st, c->memset_pending, 0)); c->memset_pending = nullptr; }
     StageScope sc(c, PSB_T_ASSIGN, c->st);
     c->launches++;
     if (launch_assign(src, len, g, scheme, precision, wscale, m0, m1, c->st)) return -1;
@@ -368,6 +375,7 @@ int sort_assign_chunk(psb_context *c, const double *src, size_t len, const Assig
     c->launches += 5;
   }
   if (consumed) PSB_CUDA(cudaEventRecord(consumed, c->st));
+  if (c->memset_pending) { PSB_CUDA(cudaStreamWaitEvent(c->st, c->memset_pending, 0)); c->memset_pending = nullptr; }
   StageScope sc(c, PSB_T_ASSIGN, c->st);
   if (launch_assign(c->sorted.as<double>(), len, g, scheme, precision, wscale, m0, m1, c->st))
     return -1;
@@ -567,20 +575,42 @@ template <typename F> double bisect_first(F pred) {
   return val(lo);
 }
 
+static bool fft_own_z(const psb_context *c, int ng, int precision) {
+  if (c->opt_fft_own_z >= 0) return c->opt_fft_own_z != 0;
+  return precision == 4 || (ng & (ng - 1)) != 0;
+}
+
+// planes per group of the L2-blocked z + y passes: the largest divisor of ng whose
+// planes (complex, in place) fit the L2 budget; ng when blocking is off
+static int fft_group_planes(const psb_context *c, int ng, int precision) {
+  if (c->opt_fft_l2_mb <= 0) return ng;
+  const size_t plane = (size_t) ng * (ng / 2 + 1) * 2 * precision;
+  int best = 1;
+  for (int p = 1; p <= ng; p++)
+    if (ng % p == 0 && p * plane <= ((size_t) c->opt_fft_l2_mb << 20)) best = p;
+  return best;
+}
+
 int ensure_plans(psb_context *c, int ng, int precision, bool need_inv) {
-  if (c->plan_ng != ng || c->plan_prec != precision) {
+  const bool own = c->opt_own_fft && fft_strided_supported(ng, precision);
+  const int zp = own ? fft_group_planes(c, ng, precision) : 0;
+  if (c->plan_ng != ng || c->plan_prec != precision || c->plan_zp != zp) {
     if (c->have_fwd) cufftDestroy(c->plan_fwd);
     if (c->have_inv) cufftDestroy(c->plan_inv);
     if (c->have_z) cufftDestroy(c->plan_z);
-    c->have_fwd = c->have_inv = c->have_z = false;
-    c->plan_ng = ng; c->plan_prec = precision;
+    if (c->have_z2) cufftDestroy(c->plan_z2);
+    c->have_fwd = c->have_inv = c->have_z = c->have_z2 = false;
+    c->plan_ng = ng; c->plan_prec = precision; c->plan_zp = zp;
   }
+  c->own_fft = own;
   const int ngk = ng / 2 + 1;
   long long n[3] = {ng, ng, ng};
   long long rembed[3] = {ng, ng, 2LL * ngk}, cembed[3] = {ng, ng, ngk};
   const long long rdist = (long long) ng * ng * 2 * ngk, cdist = (long long) ng * ng * ngk;
-  size_t ws_f = 0, ws_i = 0;
-  if (!c->have_fwd) {
+  size_t ws_f = 0, ws_i = 0, ws_z = 0;
+  // cuFFT's 3-D plan only where the hand-written strided passes do not apply (its
+  // work area is as large as the mesh for sizes that are not powers of two)
+  if (!own && !c->have_fwd) {
     PSB_CUFFT(cufftCreate(&c->plan_fwd));
     PSB_CUFFT(cufftSetAutoAllocation(c->plan_fwd, 0));
     PSB_CUFFT(cufftMakePlanMany64(c->plan_fwd, 3, n, rembed, 1, rdist, cembed, 1, cdist,
@@ -588,7 +618,7 @@ int ensure_plans(psb_context *c, int ng, int precision, bool need_inv) {
     PSB_CUFFT(cufftSetStream(c->plan_fwd, c->st));
     c->have_fwd = true;
   }
-  else PSB_CUFFT(cufftGetSize(c->plan_fwd, &ws_f));
+  else if (c->have_fwd) PSB_CUFFT(cufftGetSize(c->plan_fwd, &ws_f));
   if (need_inv && !c->have_inv) {
     PSB_CUFFT(cufftCreate(&c->plan_inv));
     PSB_CUFFT(cufftSetAutoAllocation(c->plan_inv, 0));
@@ -599,14 +629,12 @@ int ensure_plans(psb_context *c, int ng, int precision, bool need_inv) {
   }
   else if (c->have_inv) PSB_CUFFT(cufftGetSize(c->plan_inv, &ws_i));
   // the hand-written strided passes need only a batched 1-D r2c along z from cuFFT
-  c->own_fft = c->opt_own_fft && precision == 8 && ng == 1024;
-  size_t ws_z = 0;
-  if (c->own_fft && !c->have_z) {
+  if (own && !fft_own_z(c, ng, precision) && !c->have_z) {
     long long n1[1] = {ng}, re1[1] = {2LL * ngk}, ce1[1] = {ngk};
     PSB_CUFFT(cufftCreate(&c->plan_z));
     PSB_CUFFT(cufftSetAutoAllocation(c->plan_z, 0));
-    PSB_CUFFT(cufftMakePlanMany64(c->plan_z, 1, n1, re1, 1, 2LL * ngk, ce1, 1, ngk, CUFFT_D2Z,
-        (long long) ng * ng, &ws_z));
+    PSB_CUFFT(cufftMakePlanMany64(c->plan_z, 1, n1, re1, 1, 2LL * ngk, ce1, 1, ngk,
+        precision == 8 ? CUFFT_D2Z : CUFFT_R2C, (long long) zp * ng, &ws_z));
     PSB_CUFFT(cufftSetStream(c->plan_z, c->st));
     c->have_z = true;
   }
@@ -614,28 +642,69 @@ int ensure_plans(psb_context *c, int ng, int precision, bool need_inv) {
   const size_t ws = std::max(std::max(ws_f, ws_i), ws_z);
   if (c->fftwork.reserve(ws ? ws : 256)) return -1;
   if (c->have_z) PSB_CUFFT(cufftSetWorkArea(c->plan_z, c->fftwork.p));
-  PSB_CUFFT(cufftSetWorkArea(c->plan_fwd, c->fftwork.p));
+  if (c->have_z && zp < ng && c->opt_fft_streams > 1 && !c->have_z2) {
+    // a twin of the z plan on the side stream (own work area)
+    long long n1[1] = {ng}, re1[1] = {2LL * ngk}, ce1[1] = {ngk};
+    size_t ws2 = 0;
+    PSB_CUFFT(cufftCreate(&c->plan_z2));
+    PSB_CUFFT(cufftMakePlanMany64(c->plan_z2, 1, n1, re1, 1, 2LL * ngk, ce1, 1, ngk,
+        precision == 8 ? CUFFT_D2Z : CUFFT_R2C, (long long) zp * ng, &ws2));
+    PSB_CUFFT(cufftSetStream(c->plan_z2, c->st_aux));
+    c->have_z2 = true;
+  }
+  if (c->have_fwd) PSB_CUFFT(cufftSetWorkArea(c->plan_fwd, c->fftwork.p));
   if (c->have_inv) PSB_CUFFT(cufftSetWorkArea(c->plan_inv, c->fftwork.p));
   return 0;
 }
 
-int fft_forward(psb_context *c, void *mesh) {
+// skip_ok: only the binning reads the result, so the x pass may leave the
+// columns beyond the last bin edge untransformed.
+int fft_forward(psb_context *c, void *mesh, bool skip_ok) {
   StageScope sc(c, PSB_T_FFT, c->st);
   c->launches++;
   if (c->own_fft) {
-    // z: cuFFT batched 1-D r2c; y, x: hand-written strided passes (fft1024.cu).
-    // The x pass skips the columns beyond the last bin edge when only the
-    // binning reads the result (simulation boxes).
-    PSB_CUFFT(cufftExecD2Z(c->plan_z, (cufftDoubleReal *) mesh, (cufftDoubleComplex *) mesh));
-    const int ngk = c->plan_ng / 2 + 1;
-    const int fv = (int) c->opt_fft_variant;
-    StageScope own(c, PSB_T_FFT_STRIDED, c->st);
-    if (launch_fft1024_strided(mesh, ngk, 1, nullptr, nullptr, 0.0, fv, c->st)) return -1;
-    const bool skip = c->fft_skip && c->bins_ready;
-    if (launch_fft1024_strided(mesh, ngk, 0, skip ? c->bg.kax2[1] : nullptr,
-          skip ? c->bg.kax2[2] : nullptr, c->fft_k2max, fv, c->st))
+    // z: hand-written r2c over contiguous rows (or cuFFT batched 1-D r2c); y, x:
+    // hand-written strided passes (fft_strided.cu).  With an L2 budget the z and y
+    // passes run group by group over a few planes (ablation: separate launches
+    // per group cost more than the L2 hits save).
+    const int ng = c->plan_ng, ngk = ng / 2 + 1, prec = c->plan_prec, zp = c->plan_zp;
+    const size_t plane = (size_t) ng * ngk * 2 * prec;
+    // z pass: cuFFT's power-of-two double kernel is a little faster than ours
+    // (3.5 vs 4.1 ms at 1024^3); ours wins in single precision and for 1536 = 2^9 3
+    // (cuFFT: 38 ms per 1536^3 pass)
+    const bool own_z = fft_own_z(c, ng, prec);
+    const bool two = c->opt_fft_streams > 1 && zp < ng && c->have_z2 && !own_z;
+    if (two) {
+      PSB_CUDA(cudaEventRecord(c->ev_aux_go, c->st));
+      PSB_CUDA(cudaStreamWaitEvent(c->st_aux, c->ev_aux_go, 0));
+    }
+    int gi = 0;
+    for (int x0 = 0; x0 < ng; x0 += zp, gi++) {
+      char *grp = static_cast<char *>(mesh) + (size_t) x0 * plane;
+      // with two streams the z pass of one group overlaps the y pass of the other
+      const bool alt = two && (gi & 1);
+      cudaStream_t sg = alt ? c->st_aux : c->st;
+      if (own_z) {
+        if (launch_fft_rows(grp, grp, prec, ng, (long) zp * ng, 2 * (size_t) ngk, ngk, sg)) return -1;
+      }
+      else {
+        cufftHandle pz = alt ? c->plan_z2 : c->plan_z;
+        if (prec == 8) PSB_CUFFT(cufftExecD2Z(pz, (cufftDoubleReal *) grp, (cufftDoubleComplex *) grp));
+        else PSB_CUFFT(cufftExecR2C(pz, (cufftReal *) grp, (cufftComplex *) grp));
+      }
+      if (launch_fft_strided(grp, prec, ng, ngk, 1, zp, nullptr, nullptr, 0.0, sg)) return -1;
+      c->launches += 2;
+    }
+    if (two) {
+      PSB_CUDA(cudaEventRecord(c->ev_aux_done, c->st_aux));
+      PSB_CUDA(cudaStreamWaitEvent(c->st, c->ev_aux_done, 0));
+    }
+    StageScope own(c, PSB_T_FFT_STRIDED, c->st);     // the x pass
+    const bool skip = skip_ok && c->opt_fft_skip && c->bins_ready;
+    if (launch_fft_strided(mesh, prec, ng, ngk, 0, ng, skip ? c->bg.kax2[1] : nullptr,
+          skip ? c->bg.kax2[2] : nullptr, c->fft_k2max, c->st))
       return -1;
-    c->launches += 2;
+    c->launches++;
     return 0;
   }
   if (c->plan_prec == 8)
@@ -897,6 +966,11 @@ psb_context *psb_create(int device) {
   if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->st_geom, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithFlags(&c->st_copy, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->st_aux, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_aux_go, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_aux_done, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_memset[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_memset[1], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ev_geom, cudaEventDisableTiming) != cudaSuccess) {
     set_error("failed to create CUDA streams\n");
     delete c;
@@ -913,7 +987,8 @@ void psb_destroy(psb_context *c) {
   if (c->have_fwd) cufftDestroy(c->plan_fwd);
   if (c->have_inv) cufftDestroy(c->plan_inv);
   if (c->have_z) cufftDestroy(c->plan_z);
-  if (c->slab_have) { cufftDestroy(c->slab_yz); cufftDestroy(c->slab_x); }
+  if (c->have_z2) cufftDestroy(c->plan_z2);
+  if (c->slab_have) { cufftDestroy(c->slab_yz); if (!c->slab_own) cufftDestroy(c->slab_x); }
   for (int i = 0; i < 2; i++) {
     for (int j = 0; j < 2; j++) { c->part_in[i][j].release(); c->mesh[i][j].release(); }
     c->fkl[i].release(); c->fk0copy[i].release();
@@ -932,6 +1007,10 @@ void psb_destroy(psb_context *c) {
   if (c->ev_geom) cudaEventDestroy(c->ev_geom);
   if (c->st) cudaStreamDestroy(c->st);
   if (c->st_geom) cudaStreamDestroy(c->st_geom);
+  if (c->ev_aux_go) cudaEventDestroy(c->ev_aux_go);
+  if (c->ev_aux_done) cudaEventDestroy(c->ev_aux_done);
+  for (auto e : c->ev_memset) if (e) cudaEventDestroy(e);
+  if (c->st_aux) cudaStreamDestroy(c->st_aux);
   delete c;
 }
 
@@ -944,7 +1023,11 @@ int psb_set_option(psb_context *c, const char *name, long value) {
   if (!strcmp(name, "coop_variant")) { c->opt_coop_variant = value; return 0; }
   if (!strcmp(name, "xgroup")) { c->opt_xgroup = value; return 0; }
   if (!strcmp(name, "own_fft")) { c->opt_own_fft = value; return 0; }
-  if (!strcmp(name, "fft_variant")) { c->opt_fft_variant = value; return 0; }
+  if (!strcmp(name, "fft_skip")) { c->opt_fft_skip = value; return 0; }
+  if (!strcmp(name, "fft_l2_mb")) { c->opt_fft_l2_mb = value; return 0; }
+  if (!strcmp(name, "fft_streams")) { c->opt_fft_streams = value; return 0; }
+  if (!strcmp(name, "fft_own_z")) { c->opt_fft_own_z = value; return 0; }
+  if (!strcmp(name, "memset_overlap")) { c->opt_memset_overlap = value; return 0; }
   if (!strcmp(name, "survey_direct")) { c->opt_survey_direct = value; return 0; }
   if (!strcmp(name, "geom_sym")) { c->opt_geom_sym = value; return 0; }
   if (!strcmp(name, "stream")) { c->opt_stream = value; return 0; }
@@ -1031,13 +1114,31 @@ int psb_mesh(psb_context *c, const psb_params *par, const psb_cats *cats) {
   // gen_dens, src/genr_mesh.c:793-858.  Randoms are scattered with weight
   // -alpha * w into the data mesh (the reference builds a second mesh and
   // subtracts, :802-806): one pass, no extra field.
-  for (int i = 0; i < nc; i++) {
-    const int nf = par->intlace ? 2 : 1;
-    for (int f = 0; f < nf; f++) {
+  const int nf = par->intlace ? 2 : 1;
+  for (int i = 0; i < nc; i++)
+    for (int f = 0; f < nf; f++)
       if (c->mesh[i][f].reserve(mesh_bytes)) return -1;
-      StageScope sc(c, PSB_T_MEMSET, c->st);
-      PSB_CUDA(cudaMemsetAsync(c->mesh[i][f].p, 0, mesh_bytes, c->st));
+  if (c->opt_memset_overlap) {
+    // all memsets on a side stream: bandwidth-bound, they run under the
+    // latency-bound particle sort; the first scatter into a catalogue's meshes
+    // waits for them (sort_assign_chunk)
+    PSB_CUDA(cudaEventRecord(c->ev_aux_go, c->st));
+    PSB_CUDA(cudaStreamWaitEvent(c->st_aux, c->ev_aux_go, 0));
+    for (int i = 0; i < nc; i++) {
+      for (int f = 0; f < nf; f++) {
+        StageScope sc(c, PSB_T_MEMSET, c->st_aux);
+        PSB_CUDA(cudaMemsetAsync(c->mesh[i][f].p, 0, mesh_bytes, c->st_aux));
+      }
+      PSB_CUDA(cudaEventRecord(c->ev_memset[i], c->st_aux));
     }
+  }
+  for (int i = 0; i < nc; i++) {
+    if (c->opt_memset_overlap) c->memset_pending = c->ev_memset[i];
+    else
+      for (int f = 0; f < nf; f++) {
+        StageScope sc(c, PSB_T_MEMSET, c->st);
+        PSB_CUDA(cudaMemsetAsync(c->mesh[i][f].p, 0, mesh_bytes, c->st));
+      }
     void *m0 = c->mesh[i][0].p, *m1 = par->intlace ? c->mesh[i][1].p : nullptr;
     if (streaming) {
       if (stream_catalog(c, cats->data[i], cnt[i][0], g, par->assign, prec, 1.0, m0, m1)) return -1;
@@ -1048,6 +1149,8 @@ int psb_mesh(psb_context *c, const psb_params *par, const psb_cats *cats) {
           assign_catalog(c, dptr[i][1], cnt[i][1], g, par->assign, prec, -cats->alpha[i], m0, m1))
         return -1;
     }
+    // nothing was scattered (empty catalogue): later consumers still need the zeros
+    if (c->memset_pending) { PSB_CUDA(cudaStreamWaitEvent(c->st, c->memset_pending, 0)); c->memset_pending = nullptr; }
     if (par->issim) {           // src/genr_mesh.c:904-909
       const double vol = c->bsize[0] * c->bsize[1] * c->bsize[2];
       c->shot[i] = vol / cats->wdata[i];
@@ -1128,7 +1231,9 @@ psb_result *psb_power(psb_context *c, const psb_params *par) {
   double *scratch_bin = reinterpret_cast<double *>(c->binscratch.as<char>() + sb);
   // the bins are zeroed and the tables uploaded on the side stream
   if (hard(cudaStreamWaitEvent(c->st, c->ev_geom, 0))) return fail();
-  c->fft_skip = issim;          // only the binning reads delta(k) of a simulation box
+  // the x pass may skip the columns beyond the last bin edge unless the field is
+  // transformed back afterwards (interlaced survey with l > 0)
+  const bool skip_ok = !(need_ell && il);
   c->fft_k2max = c->host_tables[15 * (size_t) ng + nbin];
 
   // ---- dens_k0, src/multipole.c:435-505
@@ -1142,11 +1247,11 @@ psb_result *psb_power(psb_context *c, const psb_params *par) {
       if (c->fk0copy[i].reserve(mesh_bytes)) return fail();
       if (hard(cudaMemcpyAsync(c->fk0copy[i].p, A, mesh_bytes, cudaMemcpyDeviceToDevice, c->st)))
         return fail();
-      if (fft_forward(c, c->fk0copy[i].p)) return fail();
+      if (fft_forward(c, c->fk0copy[i].p, skip_ok)) return fail();
       Fk0[i] = c->fk0copy[i].p; Fr[i] = A;
     }
     else {
-      if (fft_forward(c, A)) return fail();
+      if (fft_forward(c, A, skip_ok)) return fail();
       Fk0[i] = A;
     }
     if (par->verbose) {
@@ -1154,7 +1259,7 @@ psb_result *psb_power(psb_context *c, const psb_params *par) {
       else printf("  Done with computing 1 FFT for l = 0 with catalog %d\n", i + 1);
     }
     if (il) {
-      if (fft_forward(c, B)) return fail();
+      if (fft_forward(c, B, skip_ok)) return fail();
       if (issim) Fk1[i] = B;    // combined on the fly inside the binning kernel
       else {
         StageScope sc(c, PSB_T_BIN, c->st);
@@ -1234,7 +1339,7 @@ psb_result *psb_power(psb_context *c, const psb_params *par) {
             if (launch_ylm_weight_r(yg, prec, Fr[i], c->fka.p, c->st)) return fail();
             c->launches++;
           }
-          if (fft_forward(c, c->fka.p)) return fail();
+          if (fft_forward(c, c->fka.p, true)) return fail();
           if (!direct) {
             StageScope sc(c, PSB_T_YLM, c->st);
             if (launch_ylm_accum_k(yg, bg, prec, c->fka.p, c->fkl[i].p, c->st)) return fail();
@@ -1450,23 +1555,42 @@ int psb_add(psb_context *c, void *dst, const void *src, size_t n, int precision)
 }
 
 static int slab_plans(psb_context *c, int ng, int nx, int prec) {
-  if (c->slab_ng == ng && c->slab_nx == nx && c->slab_prec == prec) return 0;
-  if (c->slab_have) { cufftDestroy(c->slab_yz); cufftDestroy(c->slab_x); c->slab_have = false; }
+  const bool own = c->opt_own_fft && fft_strided_supported(ng, prec);
+  if (c->slab_ng == ng && c->slab_nx == nx && c->slab_prec == prec && c->slab_own == own) return 0;
+  if (c->slab_have) {
+    cufftDestroy(c->slab_yz);
+    if (!c->slab_own) cufftDestroy(c->slab_x);
+    c->slab_have = false;
+  }
   const int ngk = ng / 2 + 1;
-  long long n2[2] = {ng, ng}, rembed[2] = {ng, 2LL * ngk}, cembed[2] = {ng, ngk};
   size_t ws = 0;
-  PSB_CUFFT(cufftCreate(&c->slab_yz));
-  PSB_CUFFT(cufftMakePlanMany64(c->slab_yz, 2, n2, rembed, 1, (long long) ng * 2 * ngk, cembed, 1,
-      (long long) ng * ngk, prec == 8 ? CUFFT_D2Z : CUFFT_R2C, nx, &ws));
-  PSB_CUFFT(cufftSetStream(c->slab_yz, c->st));
-  // after the transpose a rank holds (Ng_x, ny, Ngk): x has stride ny*Ngk
-  long long n1[1] = {ng}, embed[1] = {ng};
-  const long long lines = (long long) nx * ngk;       // ny == nx
-  PSB_CUFFT(cufftCreate(&c->slab_x));
-  PSB_CUFFT(cufftMakePlanMany64(c->slab_x, 1, n1, embed, lines, 1, embed, lines, 1,
-      prec == 8 ? CUFFT_Z2Z : CUFFT_C2C, lines, &ws));
-  PSB_CUFFT(cufftSetStream(c->slab_x, c->st));
-  c->slab_ng = ng; c->slab_nx = nx; c->slab_prec = prec; c->slab_have = true;
+  if (own) {
+    // z pass by cuFFT over groups of planes that fit the L2, y and x passes hand-written
+    int zp = 1;
+    const int cap = std::min(nx, fft_group_planes(c, ng, prec));
+    for (int p = 1; p <= cap; p++) if (nx % p == 0) zp = p;
+    long long n1[1] = {ng}, re1[1] = {2LL * ngk}, ce1[1] = {ngk};
+    PSB_CUFFT(cufftCreate(&c->slab_yz));
+    PSB_CUFFT(cufftMakePlanMany64(c->slab_yz, 1, n1, re1, 1, 2LL * ngk, ce1, 1, ngk,
+        prec == 8 ? CUFFT_D2Z : CUFFT_R2C, (long long) zp * ng, &ws));
+    PSB_CUFFT(cufftSetStream(c->slab_yz, c->st));
+    c->slab_zp = zp;
+  }
+  else {
+    long long n2[2] = {ng, ng}, rembed[2] = {ng, 2LL * ngk}, cembed[2] = {ng, ngk};
+    PSB_CUFFT(cufftCreate(&c->slab_yz));
+    PSB_CUFFT(cufftMakePlanMany64(c->slab_yz, 2, n2, rembed, 1, (long long) ng * 2 * ngk, cembed, 1,
+        (long long) ng * ngk, prec == 8 ? CUFFT_D2Z : CUFFT_R2C, nx, &ws));
+    PSB_CUFFT(cufftSetStream(c->slab_yz, c->st));
+    // after the transpose a rank holds (Ng_x, ny, Ngk): x has stride ny*Ngk
+    long long n1[1] = {ng}, embed[1] = {ng};
+    const long long lines = (long long) nx * ngk;       // ny == nx
+    PSB_CUFFT(cufftCreate(&c->slab_x));
+    PSB_CUFFT(cufftMakePlanMany64(c->slab_x, 1, n1, embed, lines, 1, embed, lines, 1,
+        prec == 8 ? CUFFT_Z2Z : CUFFT_C2C, lines, &ws));
+    PSB_CUFFT(cufftSetStream(c->slab_x, c->st));
+  }
+  c->slab_ng = ng; c->slab_nx = nx; c->slab_prec = prec; c->slab_own = own; c->slab_have = true;
   return 0;
 }
 
@@ -1477,8 +1601,24 @@ int psb_slab_fft_yz(psb_context *c, const psb_params *par, const psb_slab *sl, v
   AssignGeom g;
   if (slab_geom(c, par, sl, g)) return -1;
   PSB_CUDA(cudaSetDevice(c->device));
-  if (slab_plans(c, g.ng, g.nx, par->precision)) return -1;
-  if (par->precision == 8)
+  const int prec = par->precision;
+  if (slab_plans(c, g.ng, g.nx, prec)) return -1;
+  if (c->slab_own) {
+    const int ngk = g.ng / 2 + 1, zp = c->slab_zp;
+    const size_t plane = (size_t) g.ng * ngk * 2 * prec;
+    for (int x0 = 0; x0 < g.nx; x0 += zp) {
+      char *grp = static_cast<char *>(owned) + (size_t) x0 * plane;
+      if (fft_own_z(c, g.ng, prec)) {
+        if (launch_fft_rows(grp, grp, prec, g.ng, (long) zp * g.ng, 2 * (size_t) ngk, ngk, c->st))
+          return -1;
+      }
+      else if (prec == 8) PSB_CUFFT(cufftExecD2Z(c->slab_yz, (cufftDoubleReal *) grp, (cufftDoubleComplex *) grp));
+      else PSB_CUFFT(cufftExecR2C(c->slab_yz, (cufftReal *) grp, (cufftComplex *) grp));
+      if (launch_fft_strided(grp, prec, g.ng, ngk, 1, zp, nullptr, nullptr, 0.0, c->st)) return -1;
+      c->launches += 2;
+    }
+  }
+  else if (prec == 8)
     PSB_CUFFT(cufftExecD2Z(c->slab_yz, (cufftDoubleReal *) owned, (cufftDoubleComplex *) owned));
   else
     PSB_CUFFT(cufftExecR2C(c->slab_yz, (cufftReal *) owned, (cufftComplex *) owned));
@@ -1512,7 +1652,11 @@ int psb_slab_fft_x(psb_context *c, const psb_params *par, const psb_slab *sl, vo
   if (slab_geom(c, par, sl, g)) return -1;
   PSB_CUDA(cudaSetDevice(c->device));
   if (slab_plans(c, g.ng, g.nx, par->precision)) return -1;
-  if (par->precision == 8)
+  if (c->slab_own) {
+    if (launch_fft_strided(buf, par->precision, g.ng, g.ng / 2 + 1, 0, g.nx, nullptr, nullptr, 0.0, c->st))
+      return -1;
+  }
+  else if (par->precision == 8)
     PSB_CUFFT(cufftExecZ2Z(c->slab_x, (cufftDoubleComplex *) buf, (cufftDoubleComplex *) buf, CUFFT_FORWARD));
   else
     PSB_CUFFT(cufftExecC2C(c->slab_x, (cufftComplex *) buf, (cufftComplex *) buf, CUFFT_FORWARD));
@@ -1615,6 +1759,27 @@ int psb_generate_into(psb_context *c, double *dst_dev, size_t n, double boxsize,
 void psb_device_free(psb_context *c, void *ptr) {
   if (c) cudaSetDevice(c->device);
   if (ptr) cudaFree(ptr);
+}
+
+// one in-place forward pass of the hand-written strided FFT on caller-owned device
+// memory (building block of the slab path; tests)
+int psb_fft_axis(psb_context *c, void *data_dev, int precision, int ng, int ngk, int axis,
+    int outer_n) {
+  if (!c) { set_error("no device context\n"); return -1; }
+  if (!fft_strided_supported(ng, precision) || axis < 0 || axis > 2 || ngk < 1 || outer_n < 1 ||
+      (axis == 2 && ngk != ng / 2 + 1)) {
+    set_error("psb_fft_axis: unsupported size %d / precision %d / axis %d\n", ng, precision, axis);
+    return -1;
+  }
+  PSB_CUDA(cudaSetDevice(c->device));
+  if (axis == 2) {
+    if (launch_fft_rows(data_dev, data_dev, precision, ng, outer_n, 2 * (size_t) ngk, ngk, c->st))
+      return -1;
+  }
+  else if (launch_fft_strided(data_dev, precision, ng, ngk, axis, outer_n, nullptr, nullptr, 0.0, c->st))
+    return -1;
+  PSB_CUDA(cudaStreamSynchronize(c->st));
+  return 0;
 }
 
 int psb_copy_to_host(psb_context *c, void *dst, const void *src, size_t bytes) {

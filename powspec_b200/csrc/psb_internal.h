@@ -122,10 +122,16 @@ int launch_ylm_accum_k(const YlmGeom &g, const BinGeom &bg, int precision,
 int launch_scale(void *mesh, size_t n, double factor, int precision, cudaStream_t st);
 double ylm_norm(int l, int m);
 
-// fft1024.cu: in-place forward 1024-point pass along y (axis 1) or x (axis 0) of a
-// (1024, 1024, ngk) complex double array; optional tile skipping for the x pass
-int launch_fft1024_strided(void *data, int ngk, int axis, const double *k2a, const double *k2b,
-    double k2max, int variant, cudaStream_t st);
+// fft_strided.cu: in-place forward ng-point pass along y (axis 1, array (outer_n, ng, ngk))
+// or x (axis 0, array (ng, outer_n, ngk)) of a complex array; optional tile skipping
+// for the x pass (k2a[outer] + k2b[k] >= k2max)
+bool fft_strided_supported(int ng, int precision);
+int launch_fft_strided(void *data, int precision, int ng, int ngk, int axis, int outer_n,
+    const double *k2a, const double *k2b, double k2max, cudaStream_t st);
+
+// r2c transform of contiguous rows (the z pass)
+int launch_fft_rows(const void *src, void *dst, int precision, int ng, long nrows,
+    size_t src_pitch, size_t dst_pitch, cudaStream_t st);
 
 // generate.cu
 int launch_generate(double *out, size_t n, double boxsize, int kind, uint64_t seed,
