@@ -187,7 +187,9 @@ psb_result *psb_slab_finish(psb_context *ctx, const psb_params *par, const doubl
  * strided FFT over caller-owned device memory: complex double (precision 8) or
  * float (4), rows of ngk elements; axis 1: along y of (outer_n, ng, ngk);
  * axis 0: along x of (ng, outer_n, ngk); axis 2: real-to-complex along z of
- * outer_n contiguous rows of 2 ngk reals (ng used, ngk = ng/2 + 1), in place.
+ * outer_n contiguous rows of 2 ngk reals (ng used, ngk = ng/2 + 1), in place;
+ * axis 3: the z and y passes of outer_n planes (outer_n, ng, 2 ngk) of reals in
+ * one persistent kernel (planes handed from the z to the y pass through the L2).
  * ng in {512, 1024, 1536, 2048}. */
 int psb_fft_axis(psb_context *ctx, void *data_dev, int precision, int ng, int ngk, int axis,
     int outer_n);

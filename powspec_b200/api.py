@@ -384,6 +384,15 @@ class Context:
             raise _err(self.L, "psb_fft_axis")
         return torch.view_as_complex(tensor.view(tensor.shape[0], ng // 2 + 1, 2))
 
+    def fft_zy(self, tensor):
+        """In-place r2c along z then c2c along y of a real (nplanes, ng, 2 (ng/2+1)) CUDA
+        tensor (fused persistent kernel); returns the complex (nplanes, ng, ng/2+1) view."""
+        import torch
+        npl, ng, rl = tensor.shape
+        if self.L.psb_fft_axis(self.h, tensor.data_ptr(), tensor.element_size(), ng, rl // 2, 3, npl):
+            raise _err(self.L, "psb_fft_axis")
+        return torch.view_as_complex(tensor.view(npl, ng, rl // 2, 2))
+
     def free_catalog(self, cat):
         self.L.psb_device_free(self.h, cat[0])
 

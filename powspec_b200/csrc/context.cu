@@ -131,7 +131,7 @@ struct psb_context {
   double fft_k2max = 0;                 // last bin edge in k^2 (tile skipping of the x pass)
   int plan_ng = 0, plan_prec = 0, plan_zp = 0;
   bool have_fwd = false, have_inv = false;
-  DevBuf fftwork;
+  DevBuf fftwork, fftdone;
 
   // slab-decomposed FFT plans
   cufftHandle slab_yz = 0, slab_x = 0;
@@ -152,6 +152,7 @@ struct psb_context {
   long opt_fft_skip = 1;                // x pass skips the columns beyond the last bin edge
   long opt_fft_l2_mb = 0;               // L2 budget of a z + y plane group (0: whole mesh at once)
   long opt_fft_streams = 1;             // 2: alternate the plane groups between two streams
+  long opt_fft_fused = 0;               // z + y passes in one persistent kernel (L2 hand-over)
   long opt_fft_own_z = -1;              // hand-written r2c z pass: 1 / 0 (cuFFT batched 1-D) / -1 auto
   long opt_memset_overlap = 0;          // mesh memsets on a side stream, under the particle sort
   long opt_own_fft = 1;                 // hand-written strided FFT passes where available
@@ -629,7 +630,7 @@ int ensure_plans(psb_context *c, int ng, int precision, bool need_inv) {
   }
   else if (c->have_inv) PSB_CUFFT(cufftGetSize(c->plan_inv, &ws_i));
   // the hand-written strided passes need only a batched 1-D r2c along z from cuFFT
-  if (own && !fft_own_z(c, ng, precision) && !c->have_z) {
+  if (own && !(c->opt_fft_fused && zp == ng) && !fft_own_z(c, ng, precision) && !c->have_z) {
     long long n1[1] = {ng}, re1[1] = {2LL * ngk}, ce1[1] = {ngk};
     PSB_CUFFT(cufftCreate(&c->plan_z));
     PSB_CUFFT(cufftSetAutoAllocation(c->plan_z, 0));
@@ -673,31 +674,39 @@ int fft_forward(psb_context *c, void *mesh, bool skip_ok) {
     // (3.5 vs 4.1 ms at 1024^3); ours wins in single precision and for 1536 = 2^9 3
     // (cuFFT: 38 ms per 1536^3 pass)
     const bool own_z = fft_own_z(c, ng, prec);
-    const bool two = c->opt_fft_streams > 1 && zp < ng && c->have_z2 && !own_z;
-    if (two) {
-      PSB_CUDA(cudaEventRecord(c->ev_aux_go, c->st));
-      PSB_CUDA(cudaStreamWaitEvent(c->st_aux, c->ev_aux_go, 0));
-    }
-    int gi = 0;
-    for (int x0 = 0; x0 < ng; x0 += zp, gi++) {
-      char *grp = static_cast<char *>(mesh) + (size_t) x0 * plane;
-      // with two streams the z pass of one group overlaps the y pass of the other
-      const bool alt = two && (gi & 1);
-      cudaStream_t sg = alt ? c->st_aux : c->st;
-      if (own_z) {
-        if (launch_fft_rows(grp, grp, prec, ng, (long) zp * ng, 2 * (size_t) ngk, ngk, sg)) return -1;
-      }
-      else {
-        cufftHandle pz = alt ? c->plan_z2 : c->plan_z;
-        if (prec == 8) PSB_CUFFT(cufftExecD2Z(pz, (cufftDoubleReal *) grp, (cufftDoubleComplex *) grp));
-        else PSB_CUFFT(cufftExecR2C(pz, (cufftReal *) grp, (cufftComplex *) grp));
-      }
-      if (launch_fft_strided(grp, prec, ng, ngk, 1, zp, nullptr, nullptr, 0.0, sg)) return -1;
+    if (c->opt_fft_fused && zp == ng) {
+      // z + y in one persistent kernel, handed over plane by plane through the L2
+      if (c->fftdone.reserve(sizeof(int) * (size_t) ng)) return -1;
+      if (launch_fft_zy(mesh, prec, ng, ngk, ng, c->fftdone.as<int>(), c->st)) return -1;
       c->launches += 2;
     }
-    if (two) {
-      PSB_CUDA(cudaEventRecord(c->ev_aux_done, c->st_aux));
-      PSB_CUDA(cudaStreamWaitEvent(c->st, c->ev_aux_done, 0));
+    else {
+      const bool two = c->opt_fft_streams > 1 && zp < ng && c->have_z2 && !own_z;
+      if (two) {
+        PSB_CUDA(cudaEventRecord(c->ev_aux_go, c->st));
+        PSB_CUDA(cudaStreamWaitEvent(c->st_aux, c->ev_aux_go, 0));
+      }
+      int gi = 0;
+      for (int x0 = 0; x0 < ng; x0 += zp, gi++) {
+        char *grp = static_cast<char *>(mesh) + (size_t) x0 * plane;
+        // with two streams the z pass of one group overlaps the y pass of the other
+        const bool alt = two && (gi & 1);
+        cudaStream_t sg = alt ? c->st_aux : c->st;
+        if (own_z) {
+          if (launch_fft_rows(grp, grp, prec, ng, (long) zp * ng, 2 * (size_t) ngk, ngk, sg)) return -1;
+        }
+        else {
+          cufftHandle pz = alt ? c->plan_z2 : c->plan_z;
+          if (prec == 8) PSB_CUFFT(cufftExecD2Z(pz, (cufftDoubleReal *) grp, (cufftDoubleComplex *) grp));
+          else PSB_CUFFT(cufftExecR2C(pz, (cufftReal *) grp, (cufftComplex *) grp));
+        }
+        if (launch_fft_strided(grp, prec, ng, ngk, 1, zp, nullptr, nullptr, 0.0, sg)) return -1;
+        c->launches += 2;
+      }
+      if (two) {
+        PSB_CUDA(cudaEventRecord(c->ev_aux_done, c->st_aux));
+        PSB_CUDA(cudaStreamWaitEvent(c->st, c->ev_aux_done, 0));
+      }
     }
     StageScope own(c, PSB_T_FFT_STRIDED, c->st);     // the x pass
     const bool skip = skip_ok && c->opt_fft_skip && c->bins_ready;
@@ -1000,7 +1009,7 @@ void psb_destroy(psb_context *c) {
   }
   if (c->st_copy) cudaStreamDestroy(c->st_copy);
   c->fka.release(); c->sorted.release(); c->keys.release(); c->hist.release();
-  c->cursor.release(); c->cubtmp.release(); c->bounds_part.release(); c->fftwork.release();
+  c->cursor.release(); c->cubtmp.release(); c->bounds_part.release(); c->fftwork.release(); c->fftdone.release();
   c->tables.release(); c->binscratch.release(); c->bins.release();
   reset_timings(c);
   for (auto e : c->evpool) cudaEventDestroy(e);
@@ -1027,6 +1036,16 @@ int psb_set_option(psb_context *c, const char *name, long value) {
   if (!strcmp(name, "fft_l2_mb")) { c->opt_fft_l2_mb = value; return 0; }
   if (!strcmp(name, "fft_streams")) { c->opt_fft_streams = value; return 0; }
   if (!strcmp(name, "fft_own_z")) { c->opt_fft_own_z = value; return 0; }
+  if (!strcmp(name, "fft_fused")) { c->opt_fft_fused = value; return 0; }
+  if (!strcmp(name, "fft_variant")) { fft_set_variant((int) value); return 0; }
+  if (!strcmp(name, "l2_fetch")) {          // L2 fetch granularity hint in bytes (32 / 64 / 128)
+    if (cudaSetDevice(c->device) != cudaSuccess ||
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t) value) != cudaSuccess) {
+      set_error("cudaLimitMaxL2FetchGranularity %ld rejected\n", value);
+      return -1;
+    }
+    return 0;
+  }
   if (!strcmp(name, "memset_overlap")) { c->opt_memset_overlap = value; return 0; }
   if (!strcmp(name, "survey_direct")) { c->opt_survey_direct = value; return 0; }
   if (!strcmp(name, "geom_sym")) { c->opt_geom_sym = value; return 0; }
@@ -1603,7 +1622,12 @@ int psb_slab_fft_yz(psb_context *c, const psb_params *par, const psb_slab *sl, v
   PSB_CUDA(cudaSetDevice(c->device));
   const int prec = par->precision;
   if (slab_plans(c, g.ng, g.nx, prec)) return -1;
-  if (c->slab_own) {
+  if (c->slab_own && c->opt_fft_fused && c->slab_zp == g.nx) {
+    if (c->fftdone.reserve(sizeof(int) * (size_t) g.nx)) return -1;
+    if (launch_fft_zy(owned, prec, g.ng, g.ng / 2 + 1, g.nx, c->fftdone.as<int>(), c->st)) return -1;
+    c->launches += 2;
+  }
+  else if (c->slab_own) {
     const int ngk = g.ng / 2 + 1, zp = c->slab_zp;
     const size_t plane = (size_t) g.ng * ngk * 2 * prec;
     for (int x0 = 0; x0 < g.nx; x0 += zp) {
@@ -1766,13 +1790,17 @@ void psb_device_free(psb_context *c, void *ptr) {
 int psb_fft_axis(psb_context *c, void *data_dev, int precision, int ng, int ngk, int axis,
     int outer_n) {
   if (!c) { set_error("no device context\n"); return -1; }
-  if (!fft_strided_supported(ng, precision) || axis < 0 || axis > 2 || ngk < 1 || outer_n < 1 ||
-      (axis == 2 && ngk != ng / 2 + 1)) {
+  if (!fft_strided_supported(ng, precision) || axis < 0 || axis > 3 || ngk < 1 || outer_n < 1 ||
+      (axis >= 2 && ngk != ng / 2 + 1)) {
     set_error("psb_fft_axis: unsupported size %d / precision %d / axis %d\n", ng, precision, axis);
     return -1;
   }
   PSB_CUDA(cudaSetDevice(c->device));
-  if (axis == 2) {
+  if (axis == 3) {
+    if (c->fftdone.reserve(sizeof(int) * (size_t) outer_n)) return -1;
+    if (launch_fft_zy(data_dev, precision, ng, ngk, outer_n, c->fftdone.as<int>(), c->st)) return -1;
+  }
+  else if (axis == 2) {
     if (launch_fft_rows(data_dev, data_dev, precision, ng, outer_n, 2 * (size_t) ngk, ngk, c->st))
       return -1;
   }

@@ -49,6 +49,10 @@ namespace psb {
 
 namespace {
 
+// launch-shape ablation (context option "fft_variant"): 0 = one wide block per SM,
+// 1 = two narrower, independent blocks per SM (Ng = 1024)
+int g_fft_variant = 0;
+
 template <typename T> struct Cx { T x, y; };       // a twiddle factor
 
 // the element one thread transforms: one complex double, or two complex floats
@@ -92,6 +96,7 @@ template <> struct Mem<double> {
     if (la) v = g[off];
     return {v.x, v.y};
   }
+  static __device__ __forceinline__ cd from(double2 a, double2) { return {a.x, a.y}; }
   static __device__ __forceinline__ void store(double2 *g, size_t off, int, bool la, bool, cd v) {
     if (la) g[off] = make_double2(v.x, v.y);
   }
@@ -106,6 +111,7 @@ template <> struct Mem<float> {
     if (lb) b = g[off + tk];
     return {a.x, a.y, b.x, b.y};
   }
+  static __device__ __forceinline__ cf from(float2 a, float2 b) { return {a.x, a.y, b.x, b.y}; }
   static __device__ __forceinline__ void store(float2 *g, size_t off, int tk, bool la, bool lb, cf v) {
     if (la) g[off] = make_float2(v.x, v.y);
     if (lb) g[off + tk] = make_float2(v.z, v.w);
@@ -409,8 +415,8 @@ template <> struct RowIO<float> {
 
 // src: real rows, src_pitch reals apart; dst: complex rows, dst_pitch complex apart
 // (in place: dst == src, src_pitch == 2 dst_pitch).  nrows rows in total.
-template <typename T, int R3, int TK>
-__global__ void __launch_bounds__(Shape<R3, TK>::THREADS, 1)
+template <typename T, int R3, int TK, int MINB>
+__global__ void __launch_bounds__(Shape<R3, TK>::THREADS, MINB)
 k_fft_rows(const T *__restrict__ src, typename Mem<T>::gmem_t *__restrict__ dst, long nrows,
     size_t src_pitch, size_t dst_pitch) {
   using S = Shape<R3, TK>;
@@ -503,7 +509,7 @@ k_fft_rows(const T *__restrict__ src, typename Mem<T>::gmem_t *__restrict__ dst,
   }
 }
 
-template <typename T, int R3, int TK>
+template <typename T, int R3, int TK, int MINB>
 int launch_rows_shape(const void *src, void *dst, long nrows, size_t src_pitch, size_t dst_pitch,
     cudaStream_t st) {
   using S = Shape<R3, TK>;
@@ -513,9 +519,9 @@ int launch_rows_shape(const void *src, void *dst, long nrows, size_t src_pitch, 
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const long ntile = (nrows + TK * RowIO<T>::ROWS - 1) / (TK * RowIO<T>::ROWS);
-  const int grid = (int) std::min<long>(sms, ntile);
+  const int grid = (int) std::min<long>((long) sms * MINB, ntile);
   if (grid <= 0) return 0;
-  auto kern = k_fft_rows<T, R3, TK>;
+  auto kern = k_fft_rows<T, R3, TK, MINB>;
   PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   kern<<<grid, S::THREADS, smem, st>>>(static_cast<const T *>(src), static_cast<G *>(dst), nrows,
       src_pitch, dst_pitch);
@@ -523,14 +529,265 @@ int launch_rows_shape(const void *src, void *dst, long nrows, size_t src_pitch, 
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// z + y passes fused through the L2: ONE persistent kernel (one block per SM)
+// walks a static list of work items
+//     z(0) .. z(L-1),  [ z(p+L), y(p) ]  for p = 0 .. ng-1
+// where z(p) = the r2c row tiles of plane p and y(p) = its strided column tiles.
+// y(p) starts when a per-plane counter says all row tiles of the plane are done;
+// the plane (8.4 MB at 1024^3) is then still in the 126 MB L2, so the y pass reads
+// what the z pass wrote without going to HBM, and its in-place result overwrites
+// lines that are still dirty: the two passes cost one HBM read and one write.
+// (Doing the same with separate launches per plane group was a loss: 512 small
+// launches cost more than the L2 hits save.)
+//
+// Items are assigned round-robin (item = block + i * grid), every block works
+// through its items in increasing order and all blocks are resident, so the
+// smallest unfinished item can always run: its dependencies have smaller indices.
+// The next item's loads are issued before the current item's stores only when
+// that keeps this property (its dependencies precede the current item).
+// Both item types use the lane mapping of the strided pass (TK fastest), so the
+// twiddles and the shared-memory layout are common.  Data written by other SMs
+// inside the kernel is read with ld.global.cg (L1 is not coherent).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double2 ldcg2(const double2 *p) { return __ldcg(p); }
+__device__ __forceinline__ float2 ldcg2(const float2 *p) { return __ldcg(p); }
+
+template <typename T, int R3, int TK, int MINB>
+__global__ void __launch_bounds__(Shape<R3, TK>::THREADS, MINB)
+k_fft_zy(T *__restrict__ mesh, int ng, int ngk, int nplanes, int lag, int *__restrict__ done) {
+  using S = Shape<R3, TK>;
+  using E = El<T>;
+  using MM = Mem<T>;
+  using IO = RowIO<T>;
+  using G = typename MM::gmem_t;
+  constexpr int M = S::M, ROW = S::ROW, N = S::N, RW = IO::ROWS;
+  constexpr int RPT = TK * RW;                                  // rows per z item
+  constexpr int WIDTH = TK * MM::COLS;                          // columns per y item
+  extern __shared__ double2 sm_raw[];
+  typename MM::smem_t *sm = reinterpret_cast<typename MM::smem_t *>(sm_raw);
+  const int c = threadIdx.x % TK, u = threadIdx.x / TK;
+  typename MM::smem_t *col = sm + (size_t) c * S::PITCH;
+  const int p2 = u & 15, t1 = u >> 4;
+  Cx<T> w_t, w_t1;
+  {
+    double s, co;
+    sincospi(-2.0 * u / (double) N, &s, &co);
+    w_t = {(T) co, (T) s};
+    sincospi(-2.0 * t1 / (double) M, &s, &co);
+    w_t1 = {(T) co, (T) s};
+  }
+  const int nz = (ng + RPT - 1) / RPT, ny = (ngk + WIDTH - 1) / WIDTH, grp = nz + ny;
+  const long nitems = (long) lag * nz + (long) nplanes * grp;
+  const size_t plane_c = (size_t) ng * ngk;                     // complex elements per plane
+  // item -> (kind, plane, tile); kind 0 = z, 1 = y, -1 = nothing (z beyond the last plane)
+  auto decode = [&](long it, int &kind, int &pl, int &tl) {
+    if (it < (long) lag * nz) { kind = 0; pl = (int) (it / nz); tl = (int) (it % nz); return; }
+    const long j = it - (long) lag * nz;
+    const int gq = (int) (j / grp), r = (int) (j % grp);
+    if (r < nz) { pl = gq + lag; tl = r; kind = pl < nplanes ? 0 : -1; }
+    else { kind = 1; pl = gq; tl = r - nz; }
+  };
+  // largest item index a y item of plane pl depends on
+  auto dep_max = [&](int pl) {
+    return pl < lag ? (long) lag * nz - 1 : (long) lag * nz + (long) (pl - lag) * grp + nz - 1;
+  };
+  auto next_item = [&](long it) {
+    for (it += gridDim.x; it < nitems; it += gridDim.x) {
+      int k_, p_, t_;
+      decode(it, k_, p_, t_);
+      if (k_ >= 0) break;
+    }
+    return it;
+  };
+  auto wait_plane = [&](int pl) {
+    if (threadIdx.x == 0) {
+      while (*reinterpret_cast<volatile int *>(done + pl) < nz) __nanosleep(200);
+      __threadfence();
+    }
+    __syncthreads();
+  };
+  E a[16];
+  auto fetch = [&](int kind, int pl, int tl) {
+    if (kind == 0) {
+      const int r0 = tl * RPT + c * RW;
+      const T *rp[RW];
+      bool lv[RW];
+#pragma unroll
+      for (int j = 0; j < RW; j++) {
+        lv[j] = r0 + j < ng;
+        rp[j] = mesh + 2 * (plane_c * pl + (size_t) (lv[j] ? r0 + j : 0) * ngk) + u;
+      }
+#pragma unroll
+      for (int m = 0; m < 16; m++) a[m] = IO::load(rp, lv, M * m);
+    }
+    else {
+      const int k0 = tl * WIDTH;
+      const bool la = (k0 + c) < ngk, lb = (k0 + c + TK) < ngk;
+      const G *g = reinterpret_cast<const G *>(mesh) + plane_c * pl + k0 + c;
+#pragma unroll
+      for (int m = 0; m < 16; m++) {
+        const size_t off = (size_t) (u + M * m) * ngk;
+        if (MM::COLS == 1) {
+          G v = {};
+          if (la) v = ldcg2(g + off);
+          a[m] = Mem<T>::from(v, v);
+        }
+        else {
+          G va = {}, vb = {};
+          if (la) va = ldcg2(g + off);
+          if (lb) vb = ldcg2(g + off + TK);
+          a[m] = Mem<T>::from(va, vb);
+        }
+      }
+    }
+  };
+  long cur = blockIdx.x;
+  int kind, pl, tl;
+  if (cur < nitems) {
+    decode(cur, kind, pl, tl);
+    if (kind < 0) { cur = next_item(cur); if (cur < nitems) decode(cur, kind, pl, tl); }
+  }
+  if (cur < nitems) {
+    if (kind == 1) wait_plane(pl);
+    fetch(kind, pl, tl);
+  }
+  while (cur < nitems) {
+    // ---- passes 1 and 2, common to both kinds
+    dft16<T>(a);
+    twiddle_powers<T>(a, w_t);
+#pragma unroll
+    for (int p = 0; p < 16; p++) sm_put(&col[p * ROW + u], a[p]);
+    __syncthreads();
+#pragma unroll
+    for (int t2 = 0; t2 < 16; t2++) a[t2] = sm_get(&col[p2 * ROW + t1 + R3 * t2]);
+    __syncthreads();
+    dft16<T>(a);
+    twiddle_powers<T>(a, w_t1);
+#pragma unroll
+    for (int q1 = 0; q1 < 16; q1++) sm_put(&col[(q1 * R3 + t1) * 16 + p2], a[q1]);
+    __syncthreads();
+    // ---- the next item: prefetch now if its dependencies precede this item
+    const long nxt = next_item(cur);
+    int nkind = -1, npl = 0, ntl = 0;
+    bool fetched = false;
+    if (nxt < nitems) {
+      decode(nxt, nkind, npl, ntl);
+      if (nkind == 0 || dep_max(npl) < cur) {
+        if (nkind == 1) wait_plane(npl);
+        fetch(nkind, npl, ntl);
+        fetched = true;
+      }
+    }
+    if (kind == 1) {
+      // ---- y item: pass 3 straight to global memory
+      const int k0 = tl * WIDTH;
+      const bool la = (k0 + c) < ngk, lb = (k0 + c + TK) < ngk;
+      G *g = reinterpret_cast<G *>(mesh) + plane_c * pl + k0 + c;
+      for (int pair = u; pair < 256; pair += M) {
+        const int p3 = pair & 15, q1 = pair >> 4;
+        E d[R3];
+#pragma unroll
+        for (int tt = 0; tt < R3; tt++) d[tt] = sm_get(&col[(q1 * R3 + tt) * 16 + p3]);
+        SmallDft<T, R3>::run(d);
+#pragma unroll
+        for (int q2 = 0; q2 < R3; q2++)
+          MM::store(g, (size_t) (p3 + 16 * q1 + 256 * q2) * ngk, TK, la, lb, d[q2]);
+      }
+      __syncthreads();
+    }
+    else {
+      // ---- z item: pass 3 in place in shared memory, then un-mix the packed rows
+      for (int pair = u; pair < 256; pair += M) {
+        const int p3 = pair & 15, q1 = pair >> 4;
+        E d[R3];
+#pragma unroll
+        for (int tt = 0; tt < R3; tt++) d[tt] = sm_get(&col[(q1 * R3 + tt) * 16 + p3]);
+        SmallDft<T, R3>::run(d);
+#pragma unroll
+        for (int q2 = 0; q2 < R3; q2++) sm_put(&col[(q1 * R3 + q2) * 16 + p3], d[q2]);
+      }
+      __syncthreads();
+      G *op[RW];
+      bool olv[RW];
+#pragma unroll
+      for (int j = 0; j < RW; j++) {
+        const int r = tl * RPT + c * RW + j;
+        olv[j] = r < ng;
+        op[j] = reinterpret_cast<G *>(mesh) + plane_c * pl + (size_t) (olv[j] ? r : 0) * ngk;
+      }
+      auto slot = [](int k) { return (((k >> 4) & 15) * R3 + (k >> 8)) * 16 + (k & 15); };
+#pragma unroll
+      for (int it = 0; it <= N / 2 / M; it++) {
+        const int k = u + M * it;
+        if (k <= N / 2) {
+          const E zk = sm_get(&col[slot(k)]), zn = sm_get(&col[slot(k ? N - k : 0)]);
+          IO::store(op, olv, k, zk, zn);
+        }
+      }
+      // publish: the rows of this tile are written (barrier, then one cumulative
+      // fence by the thread that bumps the plane's counter — the grid-sync idiom)
+      __syncthreads();
+      if (threadIdx.x == 0) { __threadfence(); atomicAdd(done + pl, 1); }
+    }
+    if (nxt < nitems && !fetched) {
+      if (nkind == 1) wait_plane(npl);
+      fetch(nkind, npl, ntl);
+    }
+    cur = nxt; kind = nkind; pl = npl; tl = ntl;
+  }
+}
+
+template <typename T, int R3, int TK, int MINB>
+int launch_zy_shape(void *mesh, int ng, int ngk, int nplanes, int *done, cudaStream_t st) {
+  using S = Shape<R3, TK>;
+  const size_t smem = (size_t) TK * S::PITCH * 16;
+  auto kern = k_fft_zy<T, R3, TK, MINB>;
+  PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  int dev = 0, sms = 148, occ = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  PSB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, S::THREADS, smem));
+  if (occ < 1) { set_error("fused z + y FFT kernel does not fit an SM\n"); return -1; }
+  // every block must be resident (the items wait for each other)
+  const int grid = sms * std::min(occ, MINB);
+  const int nz = (ng + TK * RowIO<T>::ROWS - 1) / (TK * RowIO<T>::ROWS);
+  const int ny = (ngk + TK * Mem<T>::COLS - 1) / (TK * Mem<T>::COLS);
+  int lag = (grid + nz + ny) / (nz + ny) + 1;       // lag * (nz + ny) > grid
+  if (lag > nplanes) lag = nplanes;
+  PSB_CUDA(cudaMemsetAsync(done, 0, sizeof(int) * nplanes, st));
+  // cooperative launch: fails instead of deadlocking if the blocks cannot all be resident
+  T *m = static_cast<T *>(mesh);
+  void *args[] = {&m, &ng, &ngk, &nplanes, &lag, &done};
+  PSB_CUDA(cudaLaunchCooperativeKernel((const void *) kern, dim3(grid), dim3(S::THREADS), args, smem, st));
+  return 0;
+}
+
+template <typename T>
+int launch_zy_any(void *mesh, int ng, int ngk, int nplanes, int *done, cudaStream_t st) {
+  switch (ng) {
+    case 512: return launch_zy_shape<T, 2, 16, 1>(mesh, ng, ngk, nplanes, done, st);
+    case 1024:
+      if (g_fft_variant == 1) return launch_zy_shape<T, 4, 4, 2>(mesh, ng, ngk, nplanes, done, st);
+      return launch_zy_shape<T, 4, 8, 1>(mesh, ng, ngk, nplanes, done, st);
+    case 1536: return launch_zy_shape<T, 6, 4, 1>(mesh, ng, ngk, nplanes, done, st);
+    case 2048: return launch_zy_shape<T, 8, 4, 1>(mesh, ng, ngk, nplanes, done, st);
+    default:
+      set_error("no hand-written fused FFT for GRID_SIZE %d\n", ng);
+      return -1;
+  }
+}
+
 template <typename T>
 int launch_rows_any(const void *src, void *dst, int ng, long nrows, size_t src_pitch,
     size_t dst_pitch, cudaStream_t st) {
   switch (ng) {
-    case 512: return launch_rows_shape<T, 2, 16>(src, dst, nrows, src_pitch, dst_pitch, st);
-    case 1024: return launch_rows_shape<T, 4, 8>(src, dst, nrows, src_pitch, dst_pitch, st);
-    case 1536: return launch_rows_shape<T, 6, 4>(src, dst, nrows, src_pitch, dst_pitch, st);
-    case 2048: return launch_rows_shape<T, 8, 4>(src, dst, nrows, src_pitch, dst_pitch, st);
+    case 512: return launch_rows_shape<T, 2, 16, 1>(src, dst, nrows, src_pitch, dst_pitch, st);
+    case 1024:
+      if (g_fft_variant == 1) return launch_rows_shape<T, 4, 4, 2>(src, dst, nrows, src_pitch, dst_pitch, st);
+      return launch_rows_shape<T, 4, 8, 1>(src, dst, nrows, src_pitch, dst_pitch, st);
+    case 1536: return launch_rows_shape<T, 6, 4, 1>(src, dst, nrows, src_pitch, dst_pitch, st);
+    case 2048: return launch_rows_shape<T, 8, 4, 1>(src, dst, nrows, src_pitch, dst_pitch, st);
     default:
       set_error("no hand-written r2c FFT for GRID_SIZE %d\n", ng);
       return -1;
@@ -542,7 +799,9 @@ int launch_any(void *data, int ng, int ngk, int axis, int outer_n, const double 
     const double *k2b, double k2max, cudaStream_t st) {
   switch (ng) {
     case 512: return launch_shape<T, 2, 16, 1>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, st);
-    case 1024: return launch_shape<T, 4, 8, 1>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, st);
+    case 1024:
+      if (g_fft_variant == 1) return launch_shape<T, 4, 4, 2>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, st);
+      return launch_shape<T, 4, 8, 1>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, st);
     case 1536: return launch_shape<T, 6, 4, 1>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, st);
     case 2048: return launch_shape<T, 8, 4, 1>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, st);
     default:
@@ -552,6 +811,8 @@ int launch_any(void *data, int ng, int ngk, int axis, int outer_n, const double 
 }
 
 }  // namespace
+
+void fft_set_variant(int v) { g_fft_variant = v; }
 
 bool fft_strided_supported(int ng, int precision) {
   return (precision == 8 || precision == 4) && (ng == 512 || ng == 1024 || ng == 1536 || ng == 2048);
@@ -566,6 +827,14 @@ int launch_fft_strided(void *data, int precision, int ng, int ngk, int axis, int
   if (precision == 8)
     return launch_any<double>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, st);
   return launch_any<float>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, st);
+}
+
+// z and y passes of nplanes planes of a (nplanes, ng, 2 ngk) real mesh in place,
+// fused through the L2 (persistent kernel).  done: nplanes ints of device scratch.
+int launch_fft_zy(void *mesh, int precision, int ng, int ngk, int nplanes, int *done,
+    cudaStream_t st) {
+  if (precision == 8) return launch_zy_any<double>(mesh, ng, ngk, nplanes, done, st);
+  return launch_zy_any<float>(mesh, ng, ngk, nplanes, done, st);
 }
 
 // Real-to-complex forward transform of nrows contiguous rows of ng reals (the z

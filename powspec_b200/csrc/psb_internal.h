@@ -126,9 +126,13 @@ double ylm_norm(int l, int m);
 // or x (axis 0, array (ng, outer_n, ngk)) of a complex array; optional tile skipping
 // for the x pass (k2a[outer] + k2b[k] >= k2max)
 bool fft_strided_supported(int ng, int precision);
+void fft_set_variant(int v);
 int launch_fft_strided(void *data, int precision, int ng, int ngk, int axis, int outer_n,
     const double *k2a, const double *k2b, double k2max, cudaStream_t st);
 
+// z + y passes of a whole mesh in one persistent kernel (L2-resident hand-over)
+int launch_fft_zy(void *mesh, int precision, int ng, int ngk, int nplanes, int *done,
+    cudaStream_t st);
 // r2c transform of contiguous rows (the z pass)
 int launch_fft_rows(const void *src, void *dst, int precision, int ng, long nrows,
     size_t src_pitch, size_t dst_pitch, cudaStream_t st);

@@ -67,6 +67,7 @@ def main():
     ap.add_argument("--chunk", type=int, default=1 << 27, help="particles per generated chunk and rank")
     ap.add_argument("--check-counts", action="store_true")
     ap.add_argument("--kind", type=int, default=0)
+    ap.add_argument("--opt", action="append", default=[], help="context option name=value (ablations)")
     args = ap.parse_args()
 
     import torch
@@ -82,6 +83,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ctx = pb.Context(local)
+    for kv in args.opt:
+        name, val = kv.split("=")
+        ctx.set_option(name, int(val))
     s = args.scale
     out = {"config": args.config, "scale": s, "precision": args.precision, "n_gpus": world}
 
