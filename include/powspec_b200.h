@@ -71,6 +71,18 @@ enum {
   PSB_MEM_DEVICE = 1    /* already resident on `device` (bench "value" leg)    */
 };
 
+/* Coordinate conversion (RA, Dec, redshift) -> comoving Cartesian, the members of
+ * CONF that cnvt_coord() reads (src/cnvt_coord.c:440-582, src/load_conf.h:66-73).
+ * sample_z != NULL: cubic-spline interpolation of the (z, distance) table that
+ * CONF.fcdst names (the host reads the file); otherwise Legendre-Gauss
+ * integration with the order chosen for the error ecdst. */
+typedef struct {
+  double omega_m, omega_l, omega_k, eos_w;      /* CONF.omega_m/omega_l/omega_k/eos_w */
+  double ecdst;                                 /* CONF.ecdst                         */
+  const double *sample_z, *sample_d;            /* CONF.fcdst contents (host), or NULL */
+  size_t nsample;
+} psb_cosmo;
+
 /* The members of CATA (src/read_cata.h:47-59) the path reads. */
 typedef struct {
   const double *data[2];        /* CATA.data[i]: ndata[i] x {x,y,z,w}          */
@@ -81,6 +93,12 @@ typedef struct {
   double shot[2], norm[2];      /* surveys: inputs; sims: computed by the path
                                    (src/genr_mesh.c:904-909)                   */
   int memspace;                 /* PSB_MEM_HOST / PSB_MEM_DEVICE               */
+  /* optional: convert the coordinates on the device before anything else
+   * (replaces the host pass cnvt_coord(), src/powspec.c:39); dcnvt / rcnvt are
+   * CONF.dcnvt / CONF.rcnvt (DATA_CONVERT / RAND_CONVERT) per catalogue.  The
+   * caller's arrays are not modified. */
+  const psb_cosmo *cnvt;
+  int dcnvt[2], rcnvt[2];
 } psb_cats;
 
 typedef struct psb_context psb_context;         /* device, stream, buffers, FFT plans */
@@ -141,7 +159,8 @@ int psb_mesh_box(const psb_context *ctx, double bmin[3], double bsize[3], double
  * PSB_T_FFT_STRIDED is the part of it spent in the hand-written strided passes. */
 enum {
   PSB_T_H2D = 0, PSB_T_BOUNDS, PSB_T_SORT, PSB_T_MEMSET, PSB_T_ASSIGN,
-  PSB_T_FFT, PSB_T_GEOM, PSB_T_BIN, PSB_T_YLM, PSB_T_FFT_STRIDED, PSB_T_TOTAL, PSB_T_COUNT
+  PSB_T_FFT, PSB_T_GEOM, PSB_T_BIN, PSB_T_YLM, PSB_T_FFT_STRIDED, PSB_T_CNVT, PSB_T_TOTAL,
+  PSB_T_COUNT
 };
 int psb_timings(const psb_context *ctx, double *ms, int n);
 /* number of kernel launches (ours + cuFFT calls counted as 1) of the last run */
@@ -181,6 +200,14 @@ int psb_slab_bin(psb_context *ctx, const psb_params *par, const psb_slab *slab,
     const void *Fa0, const void *Fa1, const void *Fb0, const void *Fb1, double *pl_dev);
 psb_result *psb_slab_finish(psb_context *ctx, const psb_params *par, const double *pl0,
     const double *pl1, const double *xpl, const double wdata[2]);
+
+/* cnvt_coord() (src/cnvt_coord.c:549-582) on DEVICE-resident particle arrays, in
+ * place: arrays_dev[i] holds counts[i] records {RA deg, Dec deg, z, w}.  The
+ * Legendre-Gauss order is chosen from the redshift range of all the arrays
+ * (:495-511) and returned in *order (0 in interpolation mode).  Errors as the
+ * reference: negative redshift, no convergence up to order 32. */
+int psb_cnvt_coord(psb_context *ctx, const psb_cosmo *cosmo, double *const *arrays_dev,
+    const size_t *counts, int narrays, int *order);
 
 /* One in-place forward pass (sign -1, unnormalised: the convention of the FFTW
  * r2c plan of src/genr_mesh.c:738-743 along one axis) of the hand-written

@@ -76,6 +76,9 @@ psb_ref_MESH *genr_mesh(const psb_ref_CONF *conf, psb_ref_CATA *cat);
 void mesh_destroy(psb_ref_MESH *mesh);
 psb_ref_PK *powspec(const psb_ref_CONF *conf, const psb_ref_CATA *cat, psb_ref_MESH *mesh);
 void powspec_destroy(psb_ref_PK *pk);
+/* optional sixth symbol: replaces cnvt_coord.o (src/cnvt_coord.h:50) when the host
+ * is linked without it; the conversion then runs on the device inside genr_mesh */
+int cnvt_coord(const psb_ref_CONF *conf, psb_ref_CATA *cat);
 #endif
 
 #ifdef __cplusplus

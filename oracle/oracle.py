@@ -257,3 +257,65 @@ def load_oracle(kind="ref", single=False) -> Oracle:
             raise ValueError(kind)
         _cache[key] = Oracle(path)
     return _cache[key]
+
+
+# ---------------------------------------------------------------------------
+# coordinate conversion (cnvt_coord, src/cnvt_coord.c:549-582)
+# ---------------------------------------------------------------------------
+REF_CNVT_LIB = os.path.join(HERE, "_ref", "libpowspec_ref_cnvt.so")
+
+
+def have_ref_cnvt() -> bool:
+    return os.path.exists(REF_CNVT_LIB)
+
+
+def ref_cnvt(arrays, *, omega_m=0.31, omega_l=0.69, omega_k=0.0, eos_w=-1.0, ecdst=1e-8,
+             fcdst=None):
+    """The UNMODIFIED reference cnvt_coord() on copies of ``arrays`` ((N, 4) float64,
+    {RA deg, Dec deg, z, w}); ``fcdst``: path of a (z, distance) table, or None
+    for the Legendre-Gauss integration.  Up to two arrays (data catalogues)."""
+    lib = C.CDLL(REF_CNVT_LIB)
+    out = [np.array(a, dtype=np.float64, order="C", copy=True) for a in arrays]
+    n = len(out)
+    assert 1 <= n <= 2
+    ptrs = (C.c_void_p * 2)(*([o.ctypes.data for o in out] + [None] * (2 - n)))
+    cnts = (C.c_size_t * 2)(*([o.shape[0] for o in out] + [0] * (2 - n)))
+    none = (C.c_void_p * 2)(None, None)
+    zero = (C.c_size_t * 2)(0, 0)
+    yes = (C.c_int * 2)(1, 1)
+    no = (C.c_int * 2)(0, 0)
+    lib.oracle_cnvt.restype = C.c_int
+    lib.oracle_cnvt.argtypes = [C.c_double] * 5 + [C.c_char_p, C.c_int, C.c_void_p, C.c_void_p,
+                                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rc = lib.oracle_cnvt(omega_m, omega_l, omega_k, eos_w, ecdst,
+                         None if fcdst is None else os.fsencode(fcdst), n, ptrs, cnts, none, zero,
+                         yes, no)
+    if rc:
+        raise RuntimeError(f"reference cnvt_coord failed: {rc}")
+    return out
+
+
+def port_cnvt(arrays, *, omega_m=0.31, omega_l=0.69, omega_k=0.0, eos_w=-1.0, ecdst=1e-8,
+              samples=None):
+    """CPU restatement (oracle/pspec_port.c: oracle_cnvt); ``samples`` = (z[], d[]) or
+    None.  Returns (converted copies, Legendre-Gauss order)."""
+    lib = C.CDLL(build_port())
+    out = [np.array(a, dtype=np.float64, order="C", copy=True) for a in arrays]
+    n = len(out)
+    ptrs = (C.c_void_p * n)(*[o.ctypes.data for o in out])
+    cnts = (C.c_size_t * n)(*[o.shape[0] for o in out])
+    order = C.c_int(0)
+    sz = sd = None
+    ns = 0
+    if samples is not None:
+        z = np.ascontiguousarray(samples[0], dtype=np.float64)
+        d = np.ascontiguousarray(samples[1], dtype=np.float64)
+        sz, sd, ns = z.ctypes.data, d.ctypes.data, len(z)
+    lib.oracle_cnvt.restype = C.c_int
+    lib.oracle_cnvt.argtypes = [C.c_double] * 5 + [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int,
+                                                   C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    rc = lib.oracle_cnvt(omega_m, omega_l, omega_k, eos_w, ecdst, sz, sd, ns, n, ptrs, cnts,
+                         C.byref(order))
+    if rc:
+        raise RuntimeError("oracle_cnvt (port) failed")
+    return out, order.value

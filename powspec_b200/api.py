@@ -30,13 +30,14 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 powspec_assign_names = ["NGP", "CIC", "TSC", "PCS"]
 
-POWSPEC_ERR_MESH = -13      # src/define.h:122
-POWSPEC_ERR_PK = -14        # src/define.h:123
+POWSPEC_ERR_CNVT = -12      # src/define.h:120
+POWSPEC_ERR_MESH = -13      # src/define.h:121
+POWSPEC_ERR_PK = -14        # src/define.h:122
 
 (T_H2D, T_BOUNDS, T_SORT, T_MEMSET, T_ASSIGN, T_FFT, T_GEOM, T_BIN, T_YLM, T_FFT_STRIDED,
- T_TOTAL, T_COUNT) = range(12)
+ T_CNVT, T_TOTAL, T_COUNT) = range(13)
 TIMING_NAMES = ["h2d", "bounds", "sort", "memset", "assign", "fft", "geom", "bin", "ylm",
-                "fft_strided", "total"]
+                "fft_strided", "cnvt", "total"]
 
 (GET_K, GET_KEDGE, GET_KM, GET_CNT, GET_LCNT, GET_PL, GET_XPL, GET_SHOT, GET_NORM,
  GET_BMIN, GET_BSIZE, GET_BMAX) = range(12)
@@ -59,12 +60,21 @@ class _Params(C.Structure):
     ]
 
 
+class _Cosmo(C.Structure):
+    _fields_ = [
+        ("omega_m", C.c_double), ("omega_l", C.c_double), ("omega_k", C.c_double),
+        ("eos_w", C.c_double), ("ecdst", C.c_double),
+        ("sample_z", C.c_void_p), ("sample_d", C.c_void_p), ("nsample", C.c_size_t),
+    ]
+
+
 class _Cats(C.Structure):
     _fields_ = [
         ("data", C.c_void_p * 2), ("rand", C.c_void_p * 2),
         ("ndata", C.c_size_t * 2), ("nrand", C.c_size_t * 2),
         ("wdata", C.c_double * 2), ("wrand", C.c_double * 2), ("alpha", C.c_double * 2),
         ("shot", C.c_double * 2), ("norm", C.c_double * 2), ("memspace", C.c_int),
+        ("cnvt", C.POINTER(_Cosmo)), ("dcnvt", C.c_int * 2), ("rcnvt", C.c_int * 2),
     ]
 
 
@@ -114,6 +124,8 @@ def load_library():
     L.psb_device_free.argtypes = [C.c_void_p, C.c_void_p]
     L.psb_generate_into.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_int, C.c_uint64, C.c_uint64]
     L.psb_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.psb_cnvt_coord.argtypes = [C.c_void_p, C.POINTER(_Cosmo), C.c_void_p, C.c_void_p, C.c_int,
+                                 C.POINTER(C.c_int)]
     L.psb_fft_axis.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     _lib = L
     return L
@@ -146,9 +158,34 @@ class Conf:
     isauto: tuple = (True, False)
     iscross: bool = False
     verbose: bool = False
+    # coordinate conversion, read by cnvt_coord() (src/cnvt_coord.c:549-582)
+    cnvt: bool = False              # any of DATA_CONVERT / RAND_CONVERT set
+    dcnvt: tuple = (False, False)   # DATA_CONVERT per catalogue
+    rcnvt: tuple = (False, False)   # RAND_CONVERT per catalogue
+    omega_m: float = 0.31           # OMEGA_M
+    omega_l: float = 0.69           # OMEGA_LAMBDA
+    omega_k: float = 0.0            # 1 - OMEGA_M - OMEGA_LAMBDA
+    eos_w: float = -1.0             # DE_EOS_W
+    ecdst: float = 1e-8             # CMVDST_ERR
+    fcdst: tuple | None = None      # Z_CMVDST_CNVT: here the file's contents, (z[], d[])
     # not in the reference's CONF: compile-time -DSINGLE_PREC there
     precision: int = 8
     device: int = 0
+
+    def _cosmo(self):
+        """(psb_cosmo, keepalive) for cnvt_coord, or (None, None)."""
+        if not self.cnvt:
+            return None, None
+        cm = _Cosmo()
+        cm.omega_m, cm.omega_l, cm.omega_k = float(self.omega_m), float(self.omega_l), float(self.omega_k)
+        cm.eos_w, cm.ecdst = float(self.eos_w), float(self.ecdst)
+        keep = None
+        if self.fcdst is not None:
+            z = np.ascontiguousarray(self.fcdst[0], dtype=np.float64)
+            d = np.ascontiguousarray(self.fcdst[1], dtype=np.float64)
+            cm.sample_z, cm.sample_d, cm.nsample = z.ctypes.data, d.ctypes.data, len(z)
+            keep = (z, d)
+        return cm, keep
 
     def _c(self) -> _Params:
         p = _Params()
@@ -300,6 +337,11 @@ class Context:
         if len(spaces) != 1:
             raise PowspecB200Error("all catalogues must live in the same memory space")
         cats.memspace = spaces.pop()
+        cosmo, cosmo_keep = conf._cosmo()
+        if cosmo is not None:
+            cats.cnvt = C.pointer(cosmo)
+            for i in range(cata.num):
+                cats.dcnvt[i], cats.rcnvt[i] = int(conf.dcnvt[i]), int(conf.rcnvt[i])
         if self.L.psb_mesh(self.h, C.byref(p), C.byref(cats)):
             raise _err(self.L, "genr_mesh", POWSPEC_ERR_MESH)
         bmin, bsize, bmax = np.zeros(3), np.zeros(3), np.zeros(3)
@@ -364,6 +406,21 @@ class Context:
                                     int(seed), int(first_index)):
             raise _err(self.L, "psb_generate_into")
         return tensor
+
+    def cnvt_coord(self, conf: Conf, tensors):
+        """cnvt_coord() (src/cnvt_coord.c:549-582) in place on (N, 4) float64 CUDA
+        tensors {RA deg, Dec deg, z, w}; returns the Legendre-Gauss order used
+        (0 for the interpolation mode)."""
+        cosmo, keep = conf._cosmo()
+        if cosmo is None:
+            return 0
+        n = len(tensors)
+        ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in tensors])
+        cnts = (C.c_size_t * n)(*[t.shape[0] for t in tensors])
+        order = C.c_int(0)
+        if self.L.psb_cnvt_coord(self.h, C.byref(cosmo), ptrs, cnts, n, C.byref(order)):
+            raise _err(self.L, "cnvt_coord", POWSPEC_ERR_CNVT)
+        return order.value
 
     def fft_axis(self, tensor, axis: int):
         """In-place forward FFT along axis 0 or 1 of a 3-D complex CUDA tensor

@@ -131,7 +131,7 @@ struct psb_context {
   double fft_k2max = 0;                 // last bin edge in k^2 (tile skipping of the x pass)
   int plan_ng = 0, plan_prec = 0, plan_zp = 0;
   bool have_fwd = false, have_inv = false;
-  DevBuf fftwork, fftdone;
+  DevBuf fftwork, fftdone, cnvt_tab;
 
   // slab-decomposed FFT plans
   cufftHandle slab_yz = 0, slab_x = 0;
@@ -320,6 +320,59 @@ int coordinate_bounds(psb_context *c, const double *dev, size_t n, double lo[3],
       lo[a] = std::min(lo[a], h[6 * b + a]);
       hi[a] = std::max(hi[a], h[6 * b + 3 + a]);
     }
+  return 0;
+}
+
+// cnvt_coord (src/cnvt_coord.c:440-582) on device-resident arrays, in place
+int convert_arrays(psb_context *c, const psb_cosmo *cm, double *const *arr, const size_t *cnt,
+    int narr, int *order_out) {
+  if (order_out) *order_out = 0;
+  if (cm->sample_z && cm->sample_d) {
+    // interpolation of the tabulated distances (cnvt_coord_interp, :440-486)
+    const size_t nsp = cm->nsample;
+    std::vector<double> tab(3 * nsp);
+    if (nsp < 2 || cspline_second(cm->sample_z, cm->sample_d, nsp, &tab[2 * nsp])) {
+      set_error("failed to interpolate the sample points\n");
+      return -1;
+    }
+    memcpy(&tab[0], cm->sample_z, nsp * sizeof(double));
+    memcpy(&tab[nsp], cm->sample_d, nsp * sizeof(double));
+    if (c->cnvt_tab.reserve(tab.size() * sizeof(double))) return -1;
+    PSB_CUDA(cudaMemcpyAsync(c->cnvt_tab.p, tab.data(), tab.size() * sizeof(double),
+        cudaMemcpyHostToDevice, c->st));
+    PSB_CUDA(cudaStreamSynchronize(c->st));
+    const double *t = c->cnvt_tab.as<double>();
+    StageScope sc(c, PSB_T_CNVT, c->st);
+    for (int i = 0; i < narr; i++) {
+      if (launch_cnvt_interp(arr[i], cnt[i], t, t + nsp, t + 2 * nsp, nsp, c->st)) return -1;
+      c->launches++;
+    }
+    return 0;
+  }
+  // Legendre-Gauss integration (cnvt_coord_integr, :495-537): redshift range of
+  // all the catalogues (cnvt_z_sample, :160-280), order, conversion
+  double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+  for (int i = 0; i < narr; i++)
+    if (coordinate_bounds(c, arr[i], cnt[i], lo, hi)) return -1;
+  if (lo[2] < 0) {
+    set_error("invalid negative redshift in the catalogs: %g\n", lo[2]);
+    return -1;
+  }
+  if (lo[2] > hi[2]) { set_error("invalid redshift value in the catalogs\n"); return -1; }
+  const double widx = (cm->eos_w == -1) ? 0 : 3 * (1 + cm->eos_w);
+  const int order = legauss_order(cm->omega_m, cm->omega_l, cm->omega_k, widx, cm->ecdst, lo[2],
+      hi[2], 128 /* POWSPEC_INT_NUM_ZSP, src/define.h:93 */);
+  if (order == INT_MAX) {
+    set_error("failed to perform the convergency test for integrations\n");
+    return -1;
+  }
+  if (order_out) *order_out = order;
+  StageScope sc(c, PSB_T_CNVT, c->st);
+  for (int i = 0; i < narr; i++) {
+    if (launch_cnvt_integr(arr[i], cnt[i], order, cm->omega_m, cm->omega_l, cm->omega_k, widx, c->st))
+      return -1;
+    c->launches++;
+  }
   return 0;
 }
 
@@ -1009,7 +1062,7 @@ void psb_destroy(psb_context *c) {
   }
   if (c->st_copy) cudaStreamDestroy(c->st_copy);
   c->fka.release(); c->sorted.release(); c->keys.release(); c->hist.release();
-  c->cursor.release(); c->cubtmp.release(); c->bounds_part.release(); c->fftwork.release(); c->fftdone.release();
+  c->cursor.release(); c->cubtmp.release(); c->bounds_part.release(); c->fftwork.release(); c->fftdone.release(); c->cnvt_tab.release();
   c->tables.release(); c->binscratch.release(); c->bins.release();
   reset_timings(c);
   for (auto e : c->evpool) cudaEventDestroy(e);
@@ -1075,10 +1128,11 @@ int psb_mesh(psb_context *c, const psb_params *par, const psb_cats *cats) {
   // scatter chunk by chunk with PCIe and SMs overlapped; the bounds check of
   // def_box is evaluated once the stream has drained.  Surveys need the bounds
   // of every catalogue to define the box, so they are made resident first.
-  const bool streaming = par->issim && cats->memspace == PSB_MEM_HOST && c->opt_stream;
+  const bool convert = cats->cnvt != nullptr;
+  const bool streaming = par->issim && cats->memspace == PSB_MEM_HOST && c->opt_stream && !convert;
   // simulation boxes: box known in advance, bound checks deferred (computed by
   // the sort's key pass while it reads the catalogue anyway)
-  const bool deferred = par->issim && (streaming || cats->memspace == PSB_MEM_DEVICE);
+  const bool deferred = par->issim && (streaming || cats->memspace == PSB_MEM_DEVICE) && !convert;
   const double *dptr[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
   size_t cnt[2][2] = {{0, 0}, {0, 0}};
   double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
@@ -1092,13 +1146,38 @@ int psb_mesh(psb_context *c, const psb_params *par, const psb_cats *cats) {
       const size_t ch = streaming ? (size_t) std::max<long>(c->opt_stream_chunk, 1 << 16) : DEV_CHUNK;
       nchunk_total += (n + ch - 1) / ch + 1;
       if (streaming) continue;
-      if (cats->memspace == PSB_MEM_DEVICE) dptr[i][s] = src;
+      if (cats->memspace == PSB_MEM_DEVICE && !convert) dptr[i][s] = src;
+      else if (cats->memspace == PSB_MEM_DEVICE) {
+        // converted in place below: work on a copy, the caller's array stays as it is
+        if (c->part_in[i][s].reserve(n ? n * 32 : 32)) return -1;
+        PSB_CUDA(cudaMemcpyAsync(c->part_in[i][s].p, src, n * 32, cudaMemcpyDeviceToDevice, c->st));
+        dptr[i][s] = c->part_in[i][s].as<double>();
+      }
       else {
         if (upload(c, src, n, c->part_in[i][s])) return -1;
         dptr[i][s] = c->part_in[i][s].as<double>();
       }
-      if (!deferred && coordinate_bounds(c, dptr[i][s], n, lo, hi)) return -1;
+      if (!deferred && !convert && coordinate_bounds(c, dptr[i][s], n, lo, hi)) return -1;
     }
+  if (convert) {
+    // cnvt_coord(), src/powspec.c:39, on the uploaded records
+    double *arr[4];
+    size_t an[4];
+    int narr = 0;
+    for (int i = 0; i < nc; i++)
+      for (int s = 0; s < (par->issim ? 1 : 2); s++)
+        if ((s ? cats->rcnvt[i] : cats->dcnvt[i]) && cnt[i][s]) {
+          arr[narr] = const_cast<double *>(dptr[i][s]);
+          an[narr++] = cnt[i][s];
+        }
+    int order = 0;
+    if (narr && convert_arrays(c, cats->cnvt, arr, an, narr, &order)) return -1;
+    if (par->verbose && order)
+      printf("  Legendre-Gauss order %d chosen for the integration error %g\n", order, cats->cnvt->ecdst);
+    for (int i = 0; i < nc; i++)
+      for (int s = 0; s < (par->issim ? 1 : 2); s++)
+        if (coordinate_bounds(c, dptr[i][s], cnt[i][s], lo, hi)) return -1;
+  }
   if (deferred) {
     for (int a = 0; a < 3; a++) { c->bmin[a] = 0; c->bsize[a] = par->bsize[a]; }
     if (bounds_begin(c, nchunk_total)) return -1;
@@ -1807,6 +1886,18 @@ int psb_fft_axis(psb_context *c, void *data_dev, int precision, int ng, int ngk,
   else if (launch_fft_strided(data_dev, precision, ng, ngk, axis, outer_n, nullptr, nullptr, 0.0, c->st))
     return -1;
   PSB_CUDA(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+int psb_cnvt_coord(psb_context *c, const psb_cosmo *cosmo, double *const *arrays_dev,
+    const size_t *counts, int narrays, int *order) {
+  if (!c) { set_error("no device context\n"); return -1; }
+  if (!cosmo || !arrays_dev || !counts || narrays < 0) { set_error("catalogs not read\n"); return -1; }
+  PSB_CUDA(cudaSetDevice(c->device));
+  reset_timings(c);
+  if (convert_arrays(c, cosmo, arrays_dev, counts, narrays, order)) return -1;
+  PSB_CUDA(cudaStreamSynchronize(c->st));
+  collect_timings(c);
   return 0;
 }
 

@@ -137,6 +137,16 @@ int launch_fft_zy(void *mesh, int precision, int ng, int ngk, int nplanes, int *
 int launch_fft_rows(const void *src, void *dst, int precision, int ng, long nrows,
     size_t src_pitch, size_t dst_pitch, cudaStream_t st);
 
+// cnvt.cu: coordinate conversion (src/cnvt_coord.c)
+void legauss_rule(int order, double *x, double *w);
+int legauss_order(double om, double ol, double ok, double widx, double err, double zmin,
+    double zmax, int num);
+int cspline_second(const double *x, const double *y, size_t n, double *ypp);
+int launch_cnvt_integr(double *p, size_t n, int order, double om, double ol, double ok,
+    double widx, cudaStream_t st);
+int launch_cnvt_interp(double *p, size_t n, const double *z, const double *d, const double *ypp,
+    size_t nsp, cudaStream_t st);
+
 // generate.cu
 int launch_generate(double *out, size_t n, double boxsize, int kind, uint64_t seed,
     cudaStream_t st);

@@ -30,6 +30,48 @@
 
 static psb_context *g_ctx = nullptr;
 
+// Coordinate conversion requested through cnvt_coord() below: carried out on the
+// device by the next genr_mesh(), on the records it uploads anyway.
+static struct {
+  bool pending = false;
+  psb_cosmo cosmo;
+  int dcnvt[2] = {0, 0}, rcnvt[2] = {0, 0};
+  double *z = nullptr, *d = nullptr;
+} g_cnvt;
+
+// first two columns of an ASCII file, '#' comments and blank lines skipped
+// (what read_ascii_simple does for the reference, io/read_ascii.c:392-470)
+static int read_two_columns(const char *fname, double **x, double **y, size_t *num) {
+  FILE *fp = fopen(fname, "r");
+  if (!fp) { P_ERR("cannot open file for reading: `%s'\n", fname); return -1; }
+  size_t cap = 1024, n = 0;
+  double *a = static_cast<double *>(malloc(cap * sizeof(double)));
+  double *b = static_cast<double *>(malloc(cap * sizeof(double)));
+  char *line = nullptr;
+  size_t len = 0;
+  int rc = (a && b) ? 0 : -1;
+  while (!rc && getline(&line, &len, fp) != -1) {
+    const char *p = line;
+    while (*p == ' ' || *p == '\t' || *p == '\r' || *p == '\n' || *p == '\v' || *p == '\f') ++p;
+    if (*p == '#' || *p == '\0') continue;
+    if (n == cap) {
+      cap *= 2;
+      double *na = static_cast<double *>(realloc(a, cap * sizeof(double)));
+      double *nb = static_cast<double *>(realloc(b, cap * sizeof(double)));
+      if (na) a = na;
+      if (nb) b = nb;
+      if (!na || !nb) { rc = -1; break; }
+    }
+    if (sscanf(p, "%lf %lf", a + n, b + n) != 2) { P_ERR("failed to read line: %s\n", p); rc = -1; break; }
+    n++;
+  }
+  free(line);
+  fclose(fp);
+  if (rc) { free(a); free(b); return rc; }
+  *x = a; *y = b; *num = n;
+  return 0;
+}
+
 static int env_int(const char *name, int dflt) {
   const char *s = getenv(name);
   return (s && *s) ? atoi(s) : dflt;
@@ -92,7 +134,17 @@ psb_ref_MESH *genr_mesh(const psb_ref_CONF *conf, psb_ref_CATA *cat) {
     in.shot[i] = cat->shot[i];
     in.norm[i] = cat->norm[i];
   }
-  if (psb_mesh(g_ctx, &par, &in)) return nullptr;
+  if (g_cnvt.pending) {
+    in.cnvt = &g_cnvt.cosmo;
+    for (int i = 0; i < 2; i++) { in.dcnvt[i] = g_cnvt.dcnvt[i]; in.rcnvt[i] = g_cnvt.rcnvt[i]; }
+  }
+  const int mesh_rc = psb_mesh(g_ctx, &par, &in);
+  if (g_cnvt.pending) {
+    free(g_cnvt.z); free(g_cnvt.d);
+    g_cnvt.z = g_cnvt.d = nullptr;
+    g_cnvt.pending = false;
+  }
+  if (mesh_rc) return nullptr;
 
   psb_ref_MESH *mesh = static_cast<psb_ref_MESH *>(calloc(1, sizeof *mesh));
   if (!mesh) { P_ERR("failed to initalise the meshes\n"); return nullptr; }
@@ -126,6 +178,44 @@ psb_ref_MESH *genr_mesh(const psb_ref_CONF *conf, psb_ref_CATA *cat) {
 
   printf(FMT_DONE);
   return mesh;
+}
+
+// cnvt_coord(), src/cnvt_coord.c:549-582.  Optional part of the seam: when the
+// host is linked WITHOUT its own cnvt_coord.o this one is used.  It validates
+// the request, reads the distance table if one is named, and leaves the
+// conversion itself to genr_mesh(), which performs it on the device on the
+// records it uploads (the host arrays keep RA / Dec / z; genr_mesh frees them).
+// A negative redshift or a failed convergence test is therefore reported by
+// genr_mesh (POWSPEC_ERR_MESH) instead of here (POWSPEC_ERR_CNVT).
+int cnvt_coord(const psb_ref_CONF *conf, psb_ref_CATA *cat) {
+  if (!conf) { P_ERR("configuration parameters not loaded\n"); return -10; /* POWSPEC_ERR_CONF */ }
+  if (!conf->cnvt) return 0;
+  printf("Converting coordinates ...");
+  if (conf->verbose) printf("\n");
+  fflush(stdout);
+  if (!cat) { P_ERR("catalogs not read\n"); return -11; /* POWSPEC_ERR_CATA */ }
+  memset(&g_cnvt.cosmo, 0, sizeof g_cnvt.cosmo);
+  g_cnvt.cosmo.omega_m = conf->omega_m;
+  g_cnvt.cosmo.omega_l = conf->omega_l;
+  g_cnvt.cosmo.omega_k = conf->omega_k;
+  g_cnvt.cosmo.eos_w = conf->eos_w;
+  g_cnvt.cosmo.ecdst = conf->ecdst;
+  if (conf->fcdst) {
+    size_t n = 0;
+    if (conf->verbose) printf("\n  Reading samples from file: %s\n", conf->fcdst);
+    if (read_two_columns(conf->fcdst, &g_cnvt.z, &g_cnvt.d, &n)) return -12; /* POWSPEC_ERR_CNVT */
+    g_cnvt.cosmo.sample_z = g_cnvt.z;
+    g_cnvt.cosmo.sample_d = g_cnvt.d;
+    g_cnvt.cosmo.nsample = n;
+  }
+  for (int i = 0; i < cat->num && i < 2; i++) {
+    g_cnvt.dcnvt[i] = conf->dcnvt ? conf->dcnvt[i] : 0;     /* DEFAULT_CONVERT = false */
+    g_cnvt.rcnvt[i] = conf->rcnvt ? conf->rcnvt[i] : 0;
+  }
+  g_cnvt.pending = true;
+  if (conf->verbose) printf("  Conversion scheduled on the device (with the mesh generation)\n");
+  printf(FMT_DONE);
+  return 0;
 }
 
 void mesh_destroy(psb_ref_MESH *mesh) {
@@ -192,12 +282,12 @@ psb_ref_PK *powspec(const psb_ref_CONF *conf, const psb_ref_CATA *cat, psb_ref_M
   psb_result_free(res);
   if (const char *tpath = getenv("POWSPEC_B200_TIMING")) {
     static const char *names[] = {"h2d", "bounds", "sort", "memset", "assign", "fft", "geom", "bin", "ylm",
-      "fft_strided"};
+      "fft_strided", "cnvt"};
     double ms[PSB_T_COUNT];
     if (*tpath && psb_timings(g_ctx, ms, PSB_T_COUNT) > 0) {
       if (FILE *f = fopen(tpath, "a")) {
         fprintf(f, "{\"grid\": %d, \"launches\": %ld, \"stages_ms\": {", conf->gsize, psb_launch_count(g_ctx));
-        for (int i = 0; i < 10; i++) fprintf(f, "%s\"%s\": %.4f", i ? ", " : "", names[i], ms[i]);
+        for (int i = 0; i < 11; i++) fprintf(f, "%s\"%s\": %.4f", i ? ", " : "", names[i], ms[i]);
         fprintf(f, "}}\n");
         fclose(f);
       }

@@ -15,6 +15,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "POWSPEC_ref")
 OUR_BIN = os.path.join(ROOT, "oracle", "_ref", "POWSPEC_b200")
+OUR_BIN_CNVT = os.path.join(ROOT, "oracle", "_ref", "POWSPEC_b200_cnvt")
 
 
 def _need_binaries():
@@ -125,3 +126,56 @@ VERBOSE = F
     _run(REF_BIN, "survey.conf", ["-a", "ref.txt"], tmp_path, 1)
     _run(OUR_BIN, "survey.conf", ["-a", "our.txt"], tmp_path, 4)
     _compare(tmp_path / "ref.txt", tmp_path / "our.txt")
+
+
+def test_survey_from_sky_coordinates(tmp_path):
+    """DATA_CONVERT / RAND_CONVERT: (RA, Dec, z) catalogues.  POWSPEC_b200 keeps the
+    host's cnvt_coord (CPU) in front of the device path; POWSPEC_b200_cnvt is linked
+    without cnvt_coord.o, so the library's cnvt_coord is bound and the conversion
+    runs on the device inside genr_mesh.  Both must reproduce the all-reference
+    binary's output file."""
+    _need_binaries()
+    if not os.path.exists(OUR_BIN_CNVT):
+        pytest.skip("oracle/_ref/POWSPEC_b200_cnvt not built")
+
+    def cat(seed, n):
+        r = np.random.default_rng(seed)
+        ra, dec = r.uniform(100, 160, n), r.uniform(-10, 40, n)
+        z = r.uniform(0.3, 0.7, n)
+        nz = np.full(n, 3e-4)
+        return np.c_[ra, dec, z, r.uniform(0.8, 1.2, n), 1 / (1 + 1e4 * nz), nz]
+    np.savetxt(tmp_path / "data.txt", cat(5, 3000), fmt="%.17g")
+    np.savetxt(tmp_path / "rand.txt", cat(6, 15000), fmt="%.17g")
+    (tmp_path / "sky.conf").write_text("""
+DATA_CATALOG = data.txt
+RAND_CATALOG = rand.txt
+DATA_FORMATTER = "%lf %lf %lf %lf %lf %lf"
+RAND_FORMATTER = "%lf %lf %lf %lf %lf %lf"
+DATA_POSITION = [$1,$2,$3]
+RAND_POSITION = [$1,$2,$3]
+DATA_WT_COMP = $4
+RAND_WT_COMP = $4
+DATA_WT_FKP = $5
+RAND_WT_FKP = $5
+DATA_NZ = $6
+RAND_NZ = $6
+DATA_CONVERT = T
+RAND_CONVERT = T
+OMEGA_M = 0.31
+CMVDST_ERR = 1e-8
+CUBIC_SIM = F
+GRID_SIZE = 32
+PARTICLE_ASSIGN = 2
+GRID_INTERLACE = F
+MULTIPOLE = [0,2]
+KMIN = 0
+BIN_SIZE = 0.01
+OVERWRITE = 1
+VERBOSE = F
+""")
+    _run(REF_BIN, "sky.conf", ["-a", "ref.txt"], tmp_path, 1)
+    _run(OUR_BIN, "sky.conf", ["-a", "our.txt"], tmp_path, 4)
+    out = _run(OUR_BIN_CNVT, "sky.conf", ["-a", "our_dev.txt"], tmp_path, 4)
+    assert "Converting coordinates" in out
+    _compare(tmp_path / "ref.txt", tmp_path / "our.txt")
+    _compare(tmp_path / "ref.txt", tmp_path / "our_dev.txt")
