@@ -201,6 +201,22 @@ int psb_slab_bin(psb_context *ctx, const psb_params *par, const psb_slab *slab,
 psb_result *psb_slab_finish(psb_context *ctx, const psb_params *par, const double *pl0,
     const double *pl1, const double *xpl, const double wdata[2]);
 
+/* Binary catalogue ingest (the step before the boundary): a
+ * NumPy .npy file — 2-D, C order, little-endian float64 or float32, shape
+ * (N, ncols) — is streamed from the page cache to the device and turned into the
+ * particle records and catalogue sums that read_ascii_data() (io/read_ascii.c:868-902)
+ * produces from the same numbers: {x, y, z, w = wcomp * wfkp} (sims: w = wcomp),
+ * sumw = sum wcomp (CATA.wdata / wrand), sumw2 = sum w^2, sumw2n = sum wcomp wfkp^2 n(z).
+ * Columns are 0-based; -1 = absent (wcomp = 1, wfkp = 1, n(z) = 0).  The records are
+ * device memory owned by the caller (psb_device_free) and go to psb_mesh with
+ * memspace PSB_MEM_DEVICE. */
+typedef struct { int pos[3]; int wcomp, wfkp, nz; } psb_columns;
+typedef struct { size_t n; double sumw, sumw2, sumw2n; } psb_catalog_sums;
+/* header only (no device needed): rows, columns, element size in bytes */
+int psb_catalog_probe(const char *path, size_t *nrow, int *ncol, int *elem_bytes);
+int psb_catalog_load(psb_context *ctx, const char *path, const psb_columns *cols, int issim,
+    double **records_dev, psb_catalog_sums *sums);
+
 /* cnvt_coord() (src/cnvt_coord.c:549-582) on DEVICE-resident particle arrays, in
  * place: arrays_dev[i] holds counts[i] records {RA deg, Dec deg, z, w}.  The
  * Legendre-Gauss order is chosen from the redshift range of all the arrays

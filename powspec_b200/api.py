@@ -30,6 +30,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 powspec_assign_names = ["NGP", "CIC", "TSC", "PCS"]
 
+POWSPEC_ERR_CATA = -11      # src/define.h:119
 POWSPEC_ERR_CNVT = -12      # src/define.h:120
 POWSPEC_ERR_MESH = -13      # src/define.h:121
 POWSPEC_ERR_PK = -14        # src/define.h:122
@@ -66,6 +67,14 @@ class _Cosmo(C.Structure):
         ("eos_w", C.c_double), ("ecdst", C.c_double),
         ("sample_z", C.c_void_p), ("sample_d", C.c_void_p), ("nsample", C.c_size_t),
     ]
+
+
+class _Columns(C.Structure):
+    _fields_ = [("pos", C.c_int * 3), ("wcomp", C.c_int), ("wfkp", C.c_int), ("nz", C.c_int)]
+
+
+class _CatalogSums(C.Structure):
+    _fields_ = [("n", C.c_size_t), ("sumw", C.c_double), ("sumw2", C.c_double), ("sumw2n", C.c_double)]
 
 
 class _Cats(C.Structure):
@@ -124,6 +133,9 @@ def load_library():
     L.psb_device_free.argtypes = [C.c_void_p, C.c_void_p]
     L.psb_generate_into.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_int, C.c_uint64, C.c_uint64]
     L.psb_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.psb_catalog_probe.argtypes = [C.c_char_p, C.POINTER(C.c_size_t), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.psb_catalog_load.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(_Columns), C.c_int,
+                                   C.POINTER(C.c_void_p), C.POINTER(_CatalogSums)]
     L.psb_cnvt_coord.argtypes = [C.c_void_p, C.POINTER(_Cosmo), C.c_void_p, C.c_void_p, C.c_int,
                                  C.POINTER(C.c_int)]
     L.psb_fft_axis.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -406,6 +418,55 @@ class Context:
                                     int(seed), int(first_index)):
             raise _err(self.L, "psb_generate_into")
         return tensor
+
+    def load_catalog(self, path, pos=(0, 1, 2), wcomp=None, wfkp=None, nz=None, issim=True):
+        """Binary catalogue ingest (psb_catalog_load): a .npy file (N, ncols) of float64 /
+        float32 -> device records {x, y, z, w} and the sums read_ascii_data() keeps
+        (io/read_ascii.c:868-902).  Returns ((device_ptr, n), sums dict); release the
+        records with free_catalog()."""
+        cols = _Columns()
+        for i in range(3):
+            cols.pos[i] = int(pos[i])
+        cols.wcomp = -1 if wcomp is None else int(wcomp)
+        cols.wfkp = -1 if wfkp is None else int(wfkp)
+        cols.nz = -1 if nz is None else int(nz)
+        ptr = C.c_void_p()
+        sums = _CatalogSums()
+        if self.L.psb_catalog_load(self.h, os.fsencode(path), C.byref(cols), int(issim), C.byref(ptr),
+                                   C.byref(sums)):
+            raise _err(self.L, "read_cata", POWSPEC_ERR_CATA)
+        return (ptr.value, sums.n), dict(n=sums.n, sumw=sums.sumw, sumw2=sums.sumw2, sumw2n=sums.sumw2n)
+
+    def read_cata(self, conf: Conf, data_files, rand_files=None, *, pos=(0, 1, 2), wcomp=None,
+                  wfkp=None, nz=None) -> "Cata":
+        """read_cata() (src/read_cata.c:86-189) for binary catalogues: one .npy file per
+        data (and, for surveys, random) catalogue with the same column layout.  The
+        records stay on the device; wdata / wrand / alpha / shot / norm are formed
+        from the sums exactly as the reference does (:160-183)."""
+        data, rand, wd, wr, alpha, shot, norm = [], [], [], [], [], [], []
+        for i, f in enumerate(data_files):
+            d, sd = self.load_catalog(f, pos, wcomp, None if conf.issim else wfkp,
+                                      None if conf.issim else nz, conf.issim)
+            data.append(d)
+            wd.append(sd["sumw"])
+            if conf.issim:
+                continue
+            r, sr = self.load_catalog(rand_files[i], pos, wcomp, wfkp, nz, False)
+            rand.append(r)
+            wr.append(sr["sumw"])
+            if sd["sumw"] == 0 or sd["sumw2"] == 0:
+                raise PowspecB200Error("invalid completeness or FKP weights in the data catalog",
+                                       POWSPEC_ERR_CATA)
+            if sr["sumw"] == 0 or sr["sumw2"] == 0:
+                raise PowspecB200Error("invalid completeness or FKP weights in the random catalog",
+                                       POWSPEC_ERR_CATA)
+            a = sd["sumw"] / sr["sumw"]
+            alpha.append(a)
+            shot.append(sd["sumw2"] + a * a * sr["sumw2"])
+            norm.append(sd["sumw2n"] if sr["sumw2n"] == 0 else a * sr["sumw2n"])
+        if conf.issim:
+            return Cata(data=data, wdata=wd)
+        return Cata(data=data, rand=rand, wdata=wd, wrand=wr, alpha=alpha, shot=shot, norm=norm)
 
     def cnvt_coord(self, conf: Conf, tensors):
         """cnvt_coord() (src/cnvt_coord.c:549-582) in place on (N, 4) float64 CUDA

@@ -21,7 +21,7 @@ ROOT = os.path.dirname(HERE)
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libpowspec_b200.so")
 
-SOURCES = ["assign.cu", "binning.cu", "fft_strided.cu", "cnvt.cu", "generate.cu", "context.cu", "refabi.cpp"]
+SOURCES = ["assign.cu", "binning.cu", "fft_strided.cu", "cnvt.cu", "ingest.cu", "generate.cu", "context.cu", "refabi.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

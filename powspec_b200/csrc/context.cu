@@ -19,6 +19,10 @@
 #include "../../include/powspec_b200.h"
 
 #include <cufft.h>
+#include <unistd.h>
+#include <sys/stat.h>
+#include <sys/mman.h>
+#include <fcntl.h>
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
@@ -1886,6 +1890,95 @@ int psb_fft_axis(psb_context *c, void *data_dev, int precision, int ng, int ngk,
   else if (launch_fft_strided(data_dev, precision, ng, ngk, axis, outer_n, nullptr, nullptr, 0.0, c->st))
     return -1;
   PSB_CUDA(cudaStreamSynchronize(c->st));
+  return 0;
+}
+
+int psb_catalog_probe(const char *path, size_t *nrow, int *ncol, int *elem_bytes) {
+  size_t off = 0, n = 0;
+  int nc = 0, el = 0;
+  if (!path || npy_probe(path, &off, &n, &nc, &el)) return -1;
+  if (nrow) *nrow = n;
+  if (ncol) *ncol = nc;
+  if (elem_bytes) *elem_bytes = el;
+  return 0;
+}
+
+int psb_catalog_load(psb_context *c, const char *path, const psb_columns *cols, int issim,
+    double **records_dev, psb_catalog_sums *sums) {
+  if (!c) { set_error("no device context\n"); return -1; }
+  if (!path || !cols || !records_dev || !sums) { set_error("catalogs not read\n"); return -1; }
+  size_t off = 0, n = 0;
+  int ncol = 0, elem = 0;
+  if (npy_probe(path, &off, &n, &ncol, &elem)) return -1;
+  const int want[6] = {cols->pos[0], cols->pos[1], cols->pos[2], cols->wcomp, cols->wfkp, cols->nz};
+  for (int q = 0; q < 6; q++)
+    if (want[q] >= ncol || (q < 3 && want[q] < 0)) {
+      set_error("not enough columns in `%s' (%d) for column %d\n", path, ncol, want[q]);
+      return -1;
+    }
+  PSB_CUDA(cudaSetDevice(c->device));
+  reset_timings(c);
+  const size_t rowb = (size_t) ncol * elem, payload = n * rowb;
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) { set_error("cannot open file for reading: `%s'\n", path); return -1; }
+  struct stat sb;
+  if (fstat(fd, &sb) || (size_t) sb.st_size < off + payload) {
+    close(fd);
+    set_error("truncated .npy file: `%s'\n", path);
+    return -1;
+  }
+  void *map = n ? mmap(nullptr, off + payload, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
+  close(fd);
+  if (n && map == MAP_FAILED) { set_error("cannot map `%s'\n", path); return -1; }
+  if (n) madvise(map, off + payload, MADV_SEQUENTIAL);
+  const char *src = static_cast<const char *>(map) + off;
+  double *rec = nullptr;
+  DevBuf partial;
+  auto fail = [&]() { partial.release(); if (rec) cudaFree(rec); if (n) munmap(map, off + payload); return -1; };
+  if (cudaMalloc(&rec, n ? n * 32 : 32) != cudaSuccess) { set_error("out of device memory for the catalogue\n"); return fail(); }
+  const size_t CH = (size_t) 1 << 22;                       // rows per chunk
+  const size_t nchunk = (n + CH - 1) / CH;
+  const int nblk = assemble_blocks();
+  if (partial.reserve(sizeof(double) * 3 * nblk * (nchunk ? nchunk : 1))) return fail();
+  for (int s = 0; s < 2; s++) {
+    if (nchunk > (size_t) s && c->chunkbuf[s].reserve(std::min(n, CH) * rowb)) return fail();
+    if (!c->ev_filled[s]) {
+      if (cudaEventCreateWithFlags(&c->ev_filled[s], cudaEventDisableTiming) != cudaSuccess ||
+          cudaEventCreateWithFlags(&c->ev_consumed[s], cudaEventDisableTiming) != cudaSuccess)
+        return fail();
+    }
+  }
+  size_t k = 0;
+  for (size_t r0 = 0; r0 < n; r0 += CH, k++) {
+    const size_t len = std::min(CH, n - r0);
+    const int s = (int) (k & 1);
+    if (cudaStreamWaitEvent(c->st_copy, c->ev_consumed[s], 0) != cudaSuccess) return fail();
+    {
+      StageScope sc(c, PSB_T_H2D, c->st_copy);
+      if (h2d_async(c, c->chunkbuf[s].p, src + r0 * rowb, len * rowb, false, c->st_copy)) return fail();
+    }
+    if (cudaEventRecord(c->ev_filled[s], c->st_copy) != cudaSuccess ||
+        cudaStreamWaitEvent(c->st, c->ev_filled[s], 0) != cudaSuccess)
+      return fail();
+    if (launch_assemble(c->chunkbuf[s].p, elem, len, cols->pos, cols->wcomp, cols->wfkp, cols->nz, ncol,
+          issim, rec + 4 * r0, partial.as<double>() + 3 * (size_t) nblk * k, c->st))
+      return fail();
+    c->launches++;
+    if (cudaEventRecord(c->ev_consumed[s], c->st) != cudaSuccess) return fail();
+  }
+  std::vector<double> h(3 * (size_t) nblk * nchunk);
+  if (!h.empty() && cudaMemcpyAsync(h.data(), partial.p, h.size() * sizeof(double), cudaMemcpyDeviceToHost,
+        c->st) != cudaSuccess)
+    return fail();
+  if (cudaStreamSynchronize(c->st) != cudaSuccess) { set_error("catalogue ingest failed on the device\n"); return fail(); }
+  partial.release();
+  if (n) munmap(map, off + payload);
+  collect_timings(c);
+  sums->n = n; sums->sumw = sums->sumw2 = sums->sumw2n = 0;
+  for (size_t q = 0; q + 2 < h.size(); q += 3) {
+    sums->sumw += h[q]; sums->sumw2 += h[q + 1]; sums->sumw2n += h[q + 2];
+  }
+  *records_dev = rec;
   return 0;
 }
 

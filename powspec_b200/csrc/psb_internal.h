@@ -147,6 +147,12 @@ int launch_cnvt_integr(double *p, size_t n, int order, double om, double ol, dou
 int launch_cnvt_interp(double *p, size_t n, const double *z, const double *d, const double *ypp,
     size_t nsp, cudaStream_t st);
 
+// ingest.cu: binary catalogue ingest
+int npy_probe(const char *path, size_t *offset, size_t *nrow, int *ncol, int *elem);
+int assemble_blocks();
+int launch_assemble(const void *raw, int elem, size_t n, const int pos[3], int wcomp, int wfkp, int nz,
+    int ncol, int issim, double *rec, double *partial, cudaStream_t st);
+
 // generate.cu
 int launch_generate(double *out, size_t n, double boxsize, int kind, uint64_t seed,
     cudaStream_t st);
