@@ -213,9 +213,15 @@ template <typename T> __device__ __forceinline__ void dft16(El<T> (&a)[16]) {
     }
 }
 
-// a[p] *= w^p for p = 1..15, powers by a depth-4 product tree
-template <typename T> __device__ __forceinline__ void twiddle_powers(El<T> (&a)[16], Cx<T> w1) {
-  const Cx<T> w2 = wmul(w1, w1), w4 = wmul(w2, w2), w8 = wmul(w4, w4);
+// a[p] *= w^p for p = 1..15, powers by a depth-4 product tree.  w1 is the correctly
+// rounded double root and the squarings w2, w4, w8 always run in double: squaring
+// doubles the phase error each time, and a float tree from a float root doubled the
+// error of a 512^3 survey spectrum relative to cuFFT's float transform.  The
+// remaining products (at most three deep, from correctly rounded factors) run in T.
+template <typename T> __device__ __forceinline__ Cx<T> wcast(Cx<double> w) { return {(T) w.x, (T) w.y}; }
+template <typename T> __device__ __forceinline__ void twiddle_powers(El<T> (&a)[16], Cx<double> wd) {
+  const Cx<double> wd2 = wmul(wd, wd), wd4 = wmul(wd2, wd2), wd8 = wmul(wd4, wd4);
+  const Cx<T> w1 = wcast<T>(wd), w2 = wcast<T>(wd2), w4 = wcast<T>(wd4), w8 = wcast<T>(wd8);
   const Cx<T> w3 = wmul(w2, w1), w5 = wmul(w4, w1), w6 = wmul(w4, w2), w7 = wmul(w4, w3);
   a[1] = cmul(a[1], w1); a[2] = cmul(a[2], w2); a[3] = cmul(a[3], w3); a[4] = cmul(a[4], w4);
   a[5] = cmul(a[5], w5); a[6] = cmul(a[6], w6); a[7] = cmul(a[7], w7); a[8] = cmul(a[8], w8);
@@ -261,13 +267,13 @@ k_fft_strided(typename Mem<T>::gmem_t *__restrict__ data, int ngk, int outer_n, 
   typename MM::smem_t *col = sm + (size_t) c * S::PITCH;
   // roles: pass 1: t = u;  pass 2: (p2, t1) = (u % 16, u / 16)
   const int p2 = u & 15, t1 = u >> 4;
-  Cx<T> w_t, w_t1;
+  Cx<double> w_t, w_t1;
   {
     double s, co;
     sincospi(-2.0 * u / (double) S::N, &s, &co);       // w_N^t
-    w_t = {(T) co, (T) s};
+    w_t = {co, s};
     sincospi(-2.0 * t1 / (double) M, &s, &co);         // w_M^t1
-    w_t1 = {(T) co, (T) s};
+    w_t1 = {co, s};
   }
   const int ktiles = (ngk + WIDTH - 1) / WIDTH;
   const long ntile = (long) outer_n * ktiles;
@@ -430,13 +436,13 @@ k_fft_rows(const T *__restrict__ src, typename Mem<T>::gmem_t *__restrict__ dst,
   const int u = threadIdx.x % M, c = threadIdx.x / M;         // lanes run along the row
   typename Mem<T>::smem_t *col = sm + (size_t) c * S::PITCH;
   const int p2 = u & 15, t1 = u >> 4;
-  Cx<T> w_t, w_t1;
+  Cx<double> w_t, w_t1;
   {
     double s, co;
     sincospi(-2.0 * u / (double) N, &s, &co);
-    w_t = {(T) co, (T) s};
+    w_t = {co, s};
     sincospi(-2.0 * t1 / (double) M, &s, &co);
-    w_t1 = {(T) co, (T) s};
+    w_t1 = {co, s};
   }
   const long ntile = (nrows + RPT - 1) / RPT;
   E a[16];
@@ -569,13 +575,13 @@ k_fft_zy(T *__restrict__ mesh, int ng, int ngk, int nplanes, int lag, int *__res
   const int c = threadIdx.x % TK, u = threadIdx.x / TK;
   typename MM::smem_t *col = sm + (size_t) c * S::PITCH;
   const int p2 = u & 15, t1 = u >> 4;
-  Cx<T> w_t, w_t1;
+  Cx<double> w_t, w_t1;
   {
     double s, co;
     sincospi(-2.0 * u / (double) N, &s, &co);
-    w_t = {(T) co, (T) s};
+    w_t = {co, s};
     sincospi(-2.0 * t1 / (double) M, &s, &co);
-    w_t1 = {(T) co, (T) s};
+    w_t1 = {co, s};
   }
   const int nz = (ng + RPT - 1) / RPT, ny = (ngk + WIDTH - 1) / WIDTH, grp = nz + ny;
   const long nitems = (long) lag * nz + (long) nplanes * grp;
