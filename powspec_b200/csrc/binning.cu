@@ -441,10 +441,53 @@ double ylm_norm(int l, int m) {
 }
 
 // out = Fr * Y_lm(r_hat), src/mp_template.c:65-95.  Both meshes padded (rowlen).
-template <typename real>
+// One block per mesh row; a thread handles two adjacent cells per 16-byte (8-byte)
+// access and two such pairs per iteration, so four loads are in flight per thread
+// (one cell per iteration left the pass latency-bound at 3.4 TB/s).
+template <typename real> struct Pair;
+template <> struct Pair<double> { using type = double2; };
+template <> struct Pair<float> { using type = float2; };
+
+// the cells of one row, l and |m| fixed at compile time
+template <typename real, int L, int AM>
+__device__ __forceinline__ void ylm_weight_row(const YlmGeom &g, const real *__restrict__ src,
+    real *__restrict__ dst, double az, double r2, double rxy) {
+  using pair = typename Pair<real>::type;
+  const int npair = g.ng >> 1;                    // rowlen is even and rows are pair-aligned
+  auto weight = [&](int k) {
+    const double rk = (k + g.smin[2]) * g.bsize[2];
+    const double ir3 = rsqrt(r2 + rk * rk);
+    return az * ylm_polar_fixed<L, AM>(rk * ir3, rxy * ir3);
+  };
+  const pair *s2 = reinterpret_cast<const pair *>(src);
+  pair *d2 = reinterpret_cast<pair *>(dst);
+  for (int q = threadIdx.x; q < npair; q += 2 * blockDim.x) {
+    const int q1 = q + blockDim.x;
+    const bool two = q1 < npair;
+    const pair a = s2[q];
+    pair b = a;
+    if (two) b = s2[q1];
+    pair ra, rb;
+    ra.x = (real) ((double) a.x * weight(2 * q));
+    ra.y = (real) ((double) a.y * weight(2 * q + 1));
+    d2[q] = ra;
+    if (two) {
+      rb.x = (real) ((double) b.x * weight(2 * q1));
+      rb.y = (real) ((double) b.y * weight(2 * q1 + 1));
+      d2[q1] = rb;
+    }
+  }
+  if ((g.ng & 1) && threadIdx.x == 0) {                   // odd Ng: the last cell
+    const int k = g.ng - 1;
+    dst[k] = (real) ((double) src[k] * weight(k));
+  }
+}
+
+template <typename real, int L>
 __global__ void __launch_bounds__(256) k_ylm_weight_r(YlmGeom g, double nrm,
     const real *__restrict__ Fr, real *__restrict__ out) {
   const size_t nrows = (size_t) g.ng * g.ng;
+  const int am = g.m < 0 ? -g.m : g.m;
   for (size_t row = blockIdx.x; row < nrows; row += gridDim.x) {
     const int i = (int) (row / g.ng), j = (int) (row % g.ng);
     const double ri = (i + g.smin[0]) * g.bsize[0];
@@ -454,30 +497,45 @@ __global__ void __launch_bounds__(256) k_ylm_weight_r(YlmGeom g, double nrm,
     // azimuth (cos phi = ri / rxy, sin phi = rj / rxy) is constant along the row
     // (a row through the origin has no azimuth; its polar factor sin^|m| is 0 for m != 0)
     const double az = nrm * (rxy > 0.0 ? ylm_azimuth(g.m, ri / rxy, rj / rxy) : 1.0);
-    const int am = g.m < 0 ? -g.m : g.m;
     const real *src = Fr + row * g.rowlen;
     real *dst = out + row * g.rowlen;
-    for (int k = threadIdx.x; k < g.ng; k += blockDim.x) {
-      if (row == 0) { dst[k] = src[k]; continue; }      // quirk Q5 (:75-78)
-      const double rk = (k + g.smin[2]) * g.bsize[2];
-      const double ir3 = rsqrt(r2 + rk * rk);
-      const double y = az * ylm_polar(g.ell, am, rk * ir3, rxy * ir3);
-      dst[k] = (real) ((double) src[k] * y);
+    if (row == 0) {                                         // quirk Q5 (:75-78)
+      for (int k = threadIdx.x; k < g.ng; k += blockDim.x) dst[k] = src[k];
+      continue;
+    }
+    switch (am) {                                           // uniform per launch
+      case 0: ylm_weight_row<real, L, 0>(g, src, dst, az, r2, rxy); break;
+      case 1: if (L >= 1) ylm_weight_row<real, L, (L >= 1 ? 1 : 0)>(g, src, dst, az, r2, rxy); break;
+      case 2: if (L >= 2) ylm_weight_row<real, L, (L >= 2 ? 2 : 0)>(g, src, dst, az, r2, rxy); break;
+      case 3: if (L >= 3) ylm_weight_row<real, L, (L >= 3 ? 3 : 0)>(g, src, dst, az, r2, rxy); break;
+      case 4: if (L >= 4) ylm_weight_row<real, L, (L >= 4 ? 4 : 0)>(g, src, dst, az, r2, rxy); break;
+      case 5: if (L >= 5) ylm_weight_row<real, L, (L >= 5 ? 5 : 0)>(g, src, dst, az, r2, rxy); break;
+      default: if (L >= 6) ylm_weight_row<real, L, (L >= 6 ? 6 : 0)>(g, src, dst, az, r2, rxy); break;
     }
   }
+}
+
+template <typename real>
+static int launch_ylm_weight_t(const YlmGeom &g, double nrm, const real *Fr, real *out, cudaStream_t st) {
+  switch (g.ell) {
+    case 1: k_ylm_weight_r<real, 1><<<148 * 8, 256, 0, st>>>(g, nrm, Fr, out); break;
+    case 2: k_ylm_weight_r<real, 2><<<148 * 8, 256, 0, st>>>(g, nrm, Fr, out); break;
+    case 3: k_ylm_weight_r<real, 3><<<148 * 8, 256, 0, st>>>(g, nrm, Fr, out); break;
+    case 4: k_ylm_weight_r<real, 4><<<148 * 8, 256, 0, st>>>(g, nrm, Fr, out); break;
+    case 5: k_ylm_weight_r<real, 5><<<148 * 8, 256, 0, st>>>(g, nrm, Fr, out); break;
+    case 6: k_ylm_weight_r<real, 6><<<148 * 8, 256, 0, st>>>(g, nrm, Fr, out); break;
+    default: set_error("invalid multipole %d\n", g.ell); return -1;
+  }
+  PSB_CUDA(cudaGetLastError());
+  return 0;
 }
 
 int launch_ylm_weight_r(const YlmGeom &g, int precision, const void *Fr, void *out,
     cudaStream_t st) {
   const double nrm = ylm_norm(g.ell, g.m);
   if (precision == 8)
-    k_ylm_weight_r<double><<<148 * 8, 256, 0, st>>>(g, nrm,
-        static_cast<const double *>(Fr), static_cast<double *>(out));
-  else
-    k_ylm_weight_r<float><<<148 * 8, 256, 0, st>>>(g, nrm,
-        static_cast<const float *>(Fr), static_cast<float *>(out));
-  PSB_CUDA(cudaGetLastError());
-  return 0;
+    return launch_ylm_weight_t<double>(g, nrm, static_cast<const double *>(Fr), static_cast<double *>(out), st);
+  return launch_ylm_weight_t<float>(g, nrm, static_cast<const float *>(Fr), static_cast<float *>(out), st);
 }
 
 // Fkl += Fka * Y_lm(k_hat) on cells the reference marks used, src/mp_template.c:101-137

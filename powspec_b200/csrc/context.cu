@@ -162,6 +162,7 @@ struct psb_context {
   long opt_own_fft = 1;                 // hand-written strided FFT passes where available
   long opt_xgroup = 0;                  // > 0: coarse bucket sort (planes per bucket)
   long opt_strip = 64;                  // rows per strip of the sort order
+  long opt_h2d_threads = 8;             // host threads staging pageable memory into pinned buffers
   long opt_stream = 1;                  // overlap H2D with assignment for host catalogues (sims)
   long opt_stream_chunk = 1 << 24;      // particles per streamed chunk (512 MiB)
 
@@ -499,7 +500,7 @@ int h2d_async(psb_context *c, void *dst, const void *src, size_t bytes, bool pin
     c->pinned_bytes = CH;
   }
   unsigned hw = std::thread::hardware_concurrency();
-  const int nthr = (int) std::max(1u, std::min(8u, hw ? hw : 1u));
+  const int nthr = (int) std::max(1u, std::min((unsigned) std::max<long>(c->opt_h2d_threads, 1), hw ? hw : 1u));
   size_t off = 0;
   int slot = 0;
   while (off < bytes) {
@@ -1107,6 +1108,7 @@ int psb_set_option(psb_context *c, const char *name, long value) {
   if (!strcmp(name, "survey_direct")) { c->opt_survey_direct = value; return 0; }
   if (!strcmp(name, "geom_sym")) { c->opt_geom_sym = value; return 0; }
   if (!strcmp(name, "stream")) { c->opt_stream = value; return 0; }
+  if (!strcmp(name, "h2d_threads")) { c->opt_h2d_threads = value; return 0; }
   if (!strcmp(name, "stream_chunk")) { c->opt_stream_chunk = value; return 0; }
   set_error("unknown option: %s\n", name);
   return -1;

@@ -38,6 +38,26 @@ __device__ __forceinline__ double ylm_polar(int l, int am, double cost, double s
   return cur;
 }
 
+// the same recurrence with l and |m| known at compile time: the loops unroll and
+// the reciprocals fold into constants (identical sequence of operations, so the
+// result is the runtime version's bit for bit)
+template <int L, int AM>
+__device__ __forceinline__ double ylm_polar_fixed(double cost, double sint) {
+  double pmm = 1.0;
+#pragma unroll
+  for (int k = 1; k <= AM; k++) pmm *= (2 * k - 1) * sint;
+  if (L == AM) return pmm;
+  double pm1 = pmm, cur = (2 * AM + 1) * cost * pmm;
+#pragma unroll
+  for (int ll = AM + 2; ll <= L; ll++) {
+    const double inv = ll - AM == 1 ? 1.0 : ll - AM == 2 ? 0.5 : ll - AM == 3 ? 1.0 / 3.0
+        : ll - AM == 4 ? 0.25 : ll - AM == 5 ? 0.2 : ll - AM == 6 ? 1.0 / 6.0 : 1.0 / 7.0;
+    const double nxt = ((2 * ll - 1) * cost * cur - (ll + AM - 1) * pm1) * inv;
+    pm1 = cur; cur = nxt;
+  }
+  return cur;
+}
+
 __device__ __forceinline__ double ylm_real(int l, int m, double nrm, double cost,
     double sint, double cosp, double sinp) {
   return nrm * ylm_polar(l, m < 0 ? -m : m, cost, sint) * ylm_azimuth(m, cosp, sinp);
