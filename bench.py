@@ -383,7 +383,8 @@ def main():
                     "interlaced" if w["interlace"] else "single", F),
                 "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "peak_source": peak_src, "traffic": traffic,
-                "limiter": "L2 sector-request rate of the fp64 reductions (ncu lts__throughput 68 %), not HBM",
+                "limiter": "L2 atomic sector-request rate: 2.7e9 requests (18 rows x 1.5 sectors per particle) "
+                           "per launch against ~190e9/s measured by tools/red_probe.cu on B200; not HBM",
                 "algorithmic_bytes": b_assign, "launch_ms": stages.get("assign", 0.0),
                 "other_stages": {
                     "fft": {"ms": stages.get("fft", 0.0), "algorithmic_bytes": b_fft,

@@ -40,6 +40,42 @@ __global__ void __launch_bounds__(256) k_red(T *buf, size_t nelem, int iters) {
   }
 }
 
+// f32 vector reductions: every lane adds 4 consecutive floats (16-byte aligned) with one
+// RED.E.ADD.F32x4; pairs = 1: random 16-byte groups, pairs = 2: a lane issues two
+// adjacent groups (a 3-4 cell z stencil at an arbitrary offset)
+template <int PAIRS>
+__global__ void __launch_bounds__(256) k_red_v4(float *buf, size_t nelem, int iters) {
+  const size_t tid = blockIdx.x * (size_t) blockDim.x + threadIdx.x;
+  for (int it = 0; it < iters; it++) {
+    const size_t g = mix(tid * 1315423911ull + it) % (nelem / 4 - 2);
+    for (int q = 0; q < PAIRS; q++)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(buf + 4 * (g + q)), "f"(1.f),
+          "f"(1.f), "f"(1.f), "f"(1.f) : "memory");
+  }
+}
+
+template <int PAIRS>
+static void run_v4(const char *name, size_t bytes) {
+  float *buf;
+  CK(cudaMalloc(&buf, bytes));
+  CK(cudaMemset(buf, 0, bytes));
+  const size_t nelem = bytes / 4;
+  const int blocks = 148 * 8, iters = 256;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a); cudaEventCreate(&b);
+  k_red_v4<PAIRS><<<blocks, 256>>>(buf, nelem, 8);
+  CK(cudaDeviceSynchronize());
+  cudaEventRecord(a);
+  k_red_v4<PAIRS><<<blocks, 256>>>(buf, nelem, iters);
+  cudaEventRecord(b);
+  CK(cudaEventSynchronize(b));
+  float ms;
+  cudaEventElapsedTime(&ms, a, b);
+  const double ops = (double) blocks * 256 * iters * PAIRS;
+  printf("%-44s %7.3f ms  %8.2f G elem/s  %8.2f G vector-ops/s\n", name, ms, 4 * ops / ms / 1e6, ops / ms / 1e6);
+  cudaFree(buf);
+}
+
 template <typename T, int PATTERN>
 static void run(const char *name, size_t bytes) {
   T *buf;
@@ -74,5 +110,7 @@ int main() {
   run<float, 0>("f32, 1 lane per random sector, 32 MB", L2WIN);
   run<float, 1>("f32, 3 adjacent lanes, 32 MB", L2WIN);
   run<float, 2>("f32, 8 lanes per aligned sector, 32 MB", L2WIN);
+  run_v4<1>("f32x4, 1 vector per lane, random, 32 MB", L2WIN);
+  run_v4<2>("f32x4, 2 adjacent vectors per lane, 32 MB", L2WIN);
   return 0;
 }
