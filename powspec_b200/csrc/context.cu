@@ -129,8 +129,8 @@ struct psb_context {
   DevBuf fkl[2], fka, fk0copy[2];
 
   // FFT
-  cufftHandle plan_fwd = 0, plan_inv = 0, plan_z = 0, plan_z2 = 0;
-  bool have_z = false, have_z2 = false;
+  cufftHandle plan_fwd = 0, plan_inv = 0, plan_z = 0, plan_z2 = 0, plan_x = 0;
+  bool have_z = false, have_z2 = false, have_x = false;
   bool own_fft = false;                 // y/x passes by k_fft_strided (fft_strided.cu)
   double fft_k2max = 0;                 // last bin edge in k^2 (tile skipping of the x pass)
   int plan_ng = 0, plan_prec = 0, plan_zp = 0;
@@ -140,7 +140,8 @@ struct psb_context {
   // slab-decomposed FFT plans
   cufftHandle slab_yz = 0, slab_x = 0;
   int slab_ng = 0, slab_nx = 0, slab_prec = 0, slab_zp = 1;
-  bool slab_have = false, slab_own = false;
+  bool slab_have = false, slab_own = false, slab_own_x = false, slab_own_z = false;
+  bool slab_has_yz = false, slab_has_x = false;
 
   // tables and bins
   DevBuf tables, binscratch, bins;
@@ -158,6 +159,7 @@ struct psb_context {
   long opt_fft_streams = 1;             // 2: alternate the plane groups between two streams
   long opt_fft_fused = 0;               // z + y passes in one persistent kernel (L2 hand-over)
   long opt_fft_own_z = -1;              // hand-written r2c z pass: 1 / 0 (cuFFT batched 1-D) / -1 auto
+  long opt_fft_own_x = -1;              // hand-written x pass: 1 / 0 (cuFFT strided batched 1-D) / -1 auto
   long opt_memset_overlap = 0;          // mesh memsets on a side stream, under the particle sort
   long opt_own_fft = 1;                 // hand-written strided FFT passes where available
   long opt_xgroup = 0;                  // > 0: coarse bucket sort (planes per bucket)
@@ -634,9 +636,20 @@ template <typename F> double bisect_first(F pred) {
   return val(lo);
 }
 
+// Which library serves which pass is decided from the per-pass measurements on B200
+// (tools/fft_pass_bench.py, profiles/README.md): the strided y pass is always ours;
+// the r2c z pass is ours except where cuFFT's power-of-two kernels are faster (1024,
+// and 512 in double); the x pass, whose points lie a whole plane apart, is ours in
+// double up to 1536 and in single precision up to 1024 (where skipping the tiles
+// beyond the last bin edge outweighs cuFFT's faster float kernel), cuFFT's above.
 static bool fft_own_z(const psb_context *c, int ng, int precision) {
   if (c->opt_fft_own_z >= 0) return c->opt_fft_own_z != 0;
-  return precision == 4 || (ng & (ng - 1)) != 0;
+  return !(ng == 1024 || (ng == 512 && precision == 8));
+}
+
+static bool fft_own_x(const psb_context *c, int ng, int precision) {
+  if (c->opt_fft_own_x >= 0) return c->opt_fft_own_x != 0;
+  return precision == 8 ? ng <= 1536 : ng <= 1024;
 }
 
 // planes per group of the L2-blocked z + y passes: the largest divisor of ng whose
@@ -658,7 +671,8 @@ int ensure_plans(psb_context *c, int ng, int precision, bool need_inv) {
     if (c->have_inv) cufftDestroy(c->plan_inv);
     if (c->have_z) cufftDestroy(c->plan_z);
     if (c->have_z2) cufftDestroy(c->plan_z2);
-    c->have_fwd = c->have_inv = c->have_z = c->have_z2 = false;
+    if (c->have_x) cufftDestroy(c->plan_x);
+    c->have_fwd = c->have_inv = c->have_z = c->have_z2 = c->have_x = false;
     c->plan_ng = ng; c->plan_prec = precision; c->plan_zp = zp;
   }
   c->own_fft = own;
@@ -698,9 +712,23 @@ int ensure_plans(psb_context *c, int ng, int precision, bool need_inv) {
     c->have_z = true;
   }
   else if (c->have_z) PSB_CUFFT(cufftGetSize(c->plan_z, &ws_z));
-  const size_t ws = std::max(std::max(ws_f, ws_i), ws_z);
+  // cuFFT's strided batched 1-D c2c for the x pass where it is the faster one
+  size_t ws_x = 0;
+  if (own && !fft_own_x(c, ng, precision) && !c->have_x) {
+    long long n1[1] = {ng}, embed[1] = {ng};
+    const long long lines = (long long) ng * ngk;
+    PSB_CUFFT(cufftCreate(&c->plan_x));
+    PSB_CUFFT(cufftSetAutoAllocation(c->plan_x, 0));
+    PSB_CUFFT(cufftMakePlanMany64(c->plan_x, 1, n1, embed, lines, 1, embed, lines, 1,
+        precision == 8 ? CUFFT_Z2Z : CUFFT_C2C, lines, &ws_x));
+    PSB_CUFFT(cufftSetStream(c->plan_x, c->st));
+    c->have_x = true;
+  }
+  else if (c->have_x) PSB_CUFFT(cufftGetSize(c->plan_x, &ws_x));
+  const size_t ws = std::max(std::max(std::max(ws_f, ws_i), ws_z), ws_x);
   if (c->fftwork.reserve(ws ? ws : 256)) return -1;
   if (c->have_z) PSB_CUFFT(cufftSetWorkArea(c->plan_z, c->fftwork.p));
+  if (c->have_x) PSB_CUFFT(cufftSetWorkArea(c->plan_x, c->fftwork.p));
   if (c->have_z && zp < ng && c->opt_fft_streams > 1 && !c->have_z2) {
     // a twin of the z plan on the side stream (own work area)
     long long n1[1] = {ng}, re1[1] = {2LL * ngk}, ce1[1] = {ngk};
@@ -767,11 +795,18 @@ int fft_forward(psb_context *c, void *mesh, bool skip_ok) {
       }
     }
     StageScope own(c, PSB_T_FFT_STRIDED, c->st);     // the x pass
+    c->launches++;
+    if (!fft_own_x(c, ng, prec)) {
+      if (prec == 8)
+        PSB_CUFFT(cufftExecZ2Z(c->plan_x, (cufftDoubleComplex *) mesh, (cufftDoubleComplex *) mesh, CUFFT_FORWARD));
+      else
+        PSB_CUFFT(cufftExecC2C(c->plan_x, (cufftComplex *) mesh, (cufftComplex *) mesh, CUFFT_FORWARD));
+      return 0;
+    }
     const bool skip = skip_ok && c->opt_fft_skip && c->bins_ready;
     if (launch_fft_strided(mesh, prec, ng, ngk, 0, ng, skip ? c->bg.kax2[1] : nullptr,
           skip ? c->bg.kax2[2] : nullptr, c->fft_k2max, c->st))
       return -1;
-    c->launches++;
     return 0;
   }
   if (c->plan_prec == 8)
@@ -1055,7 +1090,8 @@ void psb_destroy(psb_context *c) {
   if (c->have_inv) cufftDestroy(c->plan_inv);
   if (c->have_z) cufftDestroy(c->plan_z);
   if (c->have_z2) cufftDestroy(c->plan_z2);
-  if (c->slab_have) { cufftDestroy(c->slab_yz); if (!c->slab_own) cufftDestroy(c->slab_x); }
+  if (c->have_x) cufftDestroy(c->plan_x);
+  if (c->slab_have) { if (c->slab_has_yz) cufftDestroy(c->slab_yz); if (c->slab_has_x) cufftDestroy(c->slab_x); }
   for (int i = 0; i < 2; i++) {
     for (int j = 0; j < 2; j++) { c->part_in[i][j].release(); c->mesh[i][j].release(); }
     c->fkl[i].release(); c->fk0copy[i].release();
@@ -1094,6 +1130,7 @@ int psb_set_option(psb_context *c, const char *name, long value) {
   if (!strcmp(name, "fft_l2_mb")) { c->opt_fft_l2_mb = value; return 0; }
   if (!strcmp(name, "fft_streams")) { c->opt_fft_streams = value; return 0; }
   if (!strcmp(name, "fft_own_z")) { c->opt_fft_own_z = value; return 0; }
+  if (!strcmp(name, "fft_own_x")) { c->opt_fft_own_x = value; return 0; }
   if (!strcmp(name, "fft_fused")) { c->opt_fft_fused = value; return 0; }
   if (!strcmp(name, "fft_variant")) { fft_set_variant((int) value); return 0; }
   if (!strcmp(name, "l2_fetch")) {          // L2 fetch granularity hint in bytes (32 / 64 / 128)
@@ -1660,25 +1697,33 @@ int psb_add(psb_context *c, void *dst, const void *src, size_t n, int precision)
 
 static int slab_plans(psb_context *c, int ng, int nx, int prec) {
   const bool own = c->opt_own_fft && fft_strided_supported(ng, prec);
-  if (c->slab_ng == ng && c->slab_nx == nx && c->slab_prec == prec && c->slab_own == own) return 0;
+  const bool own_x = own && fft_own_x(c, ng, prec), own_z = own && fft_own_z(c, ng, prec);
+  if (c->slab_ng == ng && c->slab_nx == nx && c->slab_prec == prec && c->slab_own == own &&
+      c->slab_own_x == own_x && c->slab_own_z == own_z)
+    return 0;
   if (c->slab_have) {
-    cufftDestroy(c->slab_yz);
-    if (!c->slab_own) cufftDestroy(c->slab_x);
-    c->slab_have = false;
+    if (c->slab_has_yz) cufftDestroy(c->slab_yz);
+    if (c->slab_has_x) cufftDestroy(c->slab_x);
+    c->slab_have = c->slab_has_yz = c->slab_has_x = false;
   }
   const int ngk = ng / 2 + 1;
   size_t ws = 0;
+  c->slab_zp = nx;
   if (own) {
-    // z pass by cuFFT over groups of planes that fit the L2, y and x passes hand-written
+    // y pass hand-written; z pass by cuFFT (1-D batched over groups of planes that fit
+    // the L2 budget, if one is set) where that is the faster one
     int zp = 1;
     const int cap = std::min(nx, fft_group_planes(c, ng, prec));
     for (int p = 1; p <= cap; p++) if (nx % p == 0) zp = p;
-    long long n1[1] = {ng}, re1[1] = {2LL * ngk}, ce1[1] = {ngk};
-    PSB_CUFFT(cufftCreate(&c->slab_yz));
-    PSB_CUFFT(cufftMakePlanMany64(c->slab_yz, 1, n1, re1, 1, 2LL * ngk, ce1, 1, ngk,
-        prec == 8 ? CUFFT_D2Z : CUFFT_R2C, (long long) zp * ng, &ws));
-    PSB_CUFFT(cufftSetStream(c->slab_yz, c->st));
     c->slab_zp = zp;
+    if (!own_z) {
+      long long n1[1] = {ng}, re1[1] = {2LL * ngk}, ce1[1] = {ngk};
+      PSB_CUFFT(cufftCreate(&c->slab_yz));
+      PSB_CUFFT(cufftMakePlanMany64(c->slab_yz, 1, n1, re1, 1, 2LL * ngk, ce1, 1, ngk,
+          prec == 8 ? CUFFT_D2Z : CUFFT_R2C, (long long) zp * ng, &ws));
+      PSB_CUFFT(cufftSetStream(c->slab_yz, c->st));
+      c->slab_has_yz = true;
+    }
   }
   else {
     long long n2[2] = {ng, ng}, rembed[2] = {ng, 2LL * ngk}, cembed[2] = {ng, ngk};
@@ -1686,6 +1731,9 @@ static int slab_plans(psb_context *c, int ng, int nx, int prec) {
     PSB_CUFFT(cufftMakePlanMany64(c->slab_yz, 2, n2, rembed, 1, (long long) ng * 2 * ngk, cembed, 1,
         (long long) ng * ngk, prec == 8 ? CUFFT_D2Z : CUFFT_R2C, nx, &ws));
     PSB_CUFFT(cufftSetStream(c->slab_yz, c->st));
+    c->slab_has_yz = true;
+  }
+  if (!own_x) {
     // after the transpose a rank holds (Ng_x, ny, Ngk): x has stride ny*Ngk
     long long n1[1] = {ng}, embed[1] = {ng};
     const long long lines = (long long) nx * ngk;       // ny == nx
@@ -1693,8 +1741,10 @@ static int slab_plans(psb_context *c, int ng, int nx, int prec) {
     PSB_CUFFT(cufftMakePlanMany64(c->slab_x, 1, n1, embed, lines, 1, embed, lines, 1,
         prec == 8 ? CUFFT_Z2Z : CUFFT_C2C, lines, &ws));
     PSB_CUFFT(cufftSetStream(c->slab_x, c->st));
+    c->slab_has_x = true;
   }
-  c->slab_ng = ng; c->slab_nx = nx; c->slab_prec = prec; c->slab_own = own; c->slab_have = true;
+  c->slab_ng = ng; c->slab_nx = nx; c->slab_prec = prec; c->slab_own = own;
+  c->slab_own_x = own_x; c->slab_own_z = own_z; c->slab_have = true;
   return 0;
 }
 
@@ -1717,7 +1767,7 @@ int psb_slab_fft_yz(psb_context *c, const psb_params *par, const psb_slab *sl, v
     const size_t plane = (size_t) g.ng * ngk * 2 * prec;
     for (int x0 = 0; x0 < g.nx; x0 += zp) {
       char *grp = static_cast<char *>(owned) + (size_t) x0 * plane;
-      if (fft_own_z(c, g.ng, prec)) {
+      if (c->slab_own_z) {
         if (launch_fft_rows(grp, grp, prec, g.ng, (long) zp * g.ng, 2 * (size_t) ngk, ngk, c->st))
           return -1;
       }
@@ -1761,7 +1811,7 @@ int psb_slab_fft_x(psb_context *c, const psb_params *par, const psb_slab *sl, vo
   if (slab_geom(c, par, sl, g)) return -1;
   PSB_CUDA(cudaSetDevice(c->device));
   if (slab_plans(c, g.ng, g.nx, par->precision)) return -1;
-  if (c->slab_own) {
+  if (c->slab_own_x) {
     if (launch_fft_strided(buf, par->precision, g.ng, g.ng / 2 + 1, 0, g.nx, nullptr, nullptr, 0.0, c->st))
       return -1;
   }
