@@ -42,6 +42,8 @@
 //   t = t1 + R3 t2, q = q1 + 16 q2  (t1, q2 < R3; t2, q1 < 16)
 //   sum_t ... = sum_t1 w_R3^{t1 q2} w_M^{t1 q1} sum_t2 B[t1 + R3 t2][p] w_16^{t2 q1}
 //                     pass 3 (radix R3)  twiddle     pass 2 (radix 16)
+// Shared memory holds B as [p][t] (row pitch M + 1); pass 2 works in place (slot
+// p (M + 1) + t1 + R3 q1 holds C[p][q1][t1]), pass 3 reads R3 consecutive slots.
 
 #include "psb_internal.h"
 
@@ -311,12 +313,12 @@ k_fft_strided(typename Mem<T>::gmem_t *__restrict__ data, int ngk, int outer_n, 
     // ---- pass 2: radix 16 over t2 (t = t1 + R3 t2) for fixed (p, t1)
 #pragma unroll
     for (int t2 = 0; t2 < 16; t2++) a[t2] = sm_get(&col[p2 * ROW + t1 + R3 * t2]);
-    __syncthreads();
     dft16<T>(a);
     twiddle_powers<T>(a, w_t1);
-    // D[q1][t1][p]: element (q1 R3 + t1) 16 + p
+    // in place: output q1 of thread (p, t1) takes the slot of its input t2 = q1, so no
+    // barrier is needed between this pass's loads and stores
 #pragma unroll
-    for (int q1 = 0; q1 < 16; q1++) sm_put(&col[(q1 * R3 + t1) * 16 + p2], a[q1]);
+    for (int q1 = 0; q1 < 16; q1++) sm_put(&col[p2 * ROW + t1 + R3 * q1], a[q1]);
     __syncthreads();
     // ---- prefetch the next tile into the (now free) registers of a[]
     const long ntl = next_tile(tile + gridDim.x);
@@ -332,7 +334,7 @@ k_fft_strided(typename Mem<T>::gmem_t *__restrict__ data, int ngk, int outer_n, 
       const int p3 = pair & 15, q1 = pair >> 4;
       E d[R3];
 #pragma unroll
-      for (int tt = 0; tt < R3; tt++) d[tt] = sm_get(&col[(q1 * R3 + tt) * 16 + p3]);
+      for (int tt = 0; tt < R3; tt++) d[tt] = sm_get(&col[p3 * ROW + tt + R3 * q1]);
       SmallDft<T, R3>::run(d);
 #pragma unroll
       for (int q2 = 0; q2 < R3; q2++)
@@ -479,29 +481,28 @@ k_fft_rows(const T *__restrict__ src, typename Mem<T>::gmem_t *__restrict__ dst,
     // ---- pass 2: radix 16 over t2
 #pragma unroll
     for (int t2 = 0; t2 < 16; t2++) a[t2] = sm_get(&col[p2 * ROW + t1 + R3 * t2]);
-    __syncthreads();
     dft16<T>(a);
     twiddle_powers<T>(a, w_t1);
 #pragma unroll
-    for (int q1 = 0; q1 < 16; q1++) sm_put(&col[(q1 * R3 + t1) * 16 + p2], a[q1]);
+    for (int q1 = 0; q1 < 16; q1++) sm_put(&col[p2 * ROW + t1 + R3 * q1], a[q1]);
     __syncthreads();
     // ---- next tile's loads in flight during the last pass and the un-mixing
     const long ntl = tile + gridDim.x;
     if (ntl < ntile) fetch(ntl);
     // ---- pass 3: radix R3, in place in shared memory (a thread reads and writes
-    // the same R3 slots): Z[p + 16 q1 + 256 q2] lands at (q1 R3 + q2) 16 + p
+    // the same R3 slots): Z[p + 16 q1 + 256 q2] lands at p (M + 1) + R3 q1 + q2
     for (int pair = u; pair < 256; pair += M) {
       const int p3 = pair & 15, q1 = pair >> 4;
       E d[R3];
 #pragma unroll
-      for (int tt = 0; tt < R3; tt++) d[tt] = sm_get(&col[(q1 * R3 + tt) * 16 + p3]);
+      for (int tt = 0; tt < R3; tt++) d[tt] = sm_get(&col[p3 * ROW + tt + R3 * q1]);
       SmallDft<T, R3>::run(d);
 #pragma unroll
-      for (int q2 = 0; q2 < R3; q2++) sm_put(&col[(q1 * R3 + q2) * 16 + p3], d[q2]);
+      for (int q2 = 0; q2 < R3; q2++) sm_put(&col[p3 * ROW + q2 + R3 * q1], d[q2]);
     }
     __syncthreads();
     // ---- un-mix the rows and store k = 0 .. N/2
-    auto slot = [](int k) { return (((k >> 4) & 15) * R3 + (k >> 8)) * 16 + (k & 15); };
+    auto slot = [](int k) { return (k & 15) * ROW + (k >> 8) + R3 * ((k >> 4) & 15); };
 #pragma unroll
     for (int it = 0; it <= N / 2 / M; it++) {
       const int k = u + M * it;
@@ -667,11 +668,10 @@ k_fft_zy(T *__restrict__ mesh, int ng, int ngk, int nplanes, int lag, int *__res
     __syncthreads();
 #pragma unroll
     for (int t2 = 0; t2 < 16; t2++) a[t2] = sm_get(&col[p2 * ROW + t1 + R3 * t2]);
-    __syncthreads();
     dft16<T>(a);
     twiddle_powers<T>(a, w_t1);
 #pragma unroll
-    for (int q1 = 0; q1 < 16; q1++) sm_put(&col[(q1 * R3 + t1) * 16 + p2], a[q1]);
+    for (int q1 = 0; q1 < 16; q1++) sm_put(&col[p2 * ROW + t1 + R3 * q1], a[q1]);
     __syncthreads();
     // ---- the next item: prefetch now if its dependencies precede this item
     const long nxt = next_item(cur);
@@ -694,7 +694,7 @@ k_fft_zy(T *__restrict__ mesh, int ng, int ngk, int nplanes, int lag, int *__res
         const int p3 = pair & 15, q1 = pair >> 4;
         E d[R3];
 #pragma unroll
-        for (int tt = 0; tt < R3; tt++) d[tt] = sm_get(&col[(q1 * R3 + tt) * 16 + p3]);
+        for (int tt = 0; tt < R3; tt++) d[tt] = sm_get(&col[p3 * ROW + tt + R3 * q1]);
         SmallDft<T, R3>::run(d);
 #pragma unroll
         for (int q2 = 0; q2 < R3; q2++)
@@ -708,10 +708,10 @@ k_fft_zy(T *__restrict__ mesh, int ng, int ngk, int nplanes, int lag, int *__res
         const int p3 = pair & 15, q1 = pair >> 4;
         E d[R3];
 #pragma unroll
-        for (int tt = 0; tt < R3; tt++) d[tt] = sm_get(&col[(q1 * R3 + tt) * 16 + p3]);
+        for (int tt = 0; tt < R3; tt++) d[tt] = sm_get(&col[p3 * ROW + tt + R3 * q1]);
         SmallDft<T, R3>::run(d);
 #pragma unroll
-        for (int q2 = 0; q2 < R3; q2++) sm_put(&col[(q1 * R3 + q2) * 16 + p3], d[q2]);
+        for (int q2 = 0; q2 < R3; q2++) sm_put(&col[p3 * ROW + q2 + R3 * q1], d[q2]);
       }
       __syncthreads();
       G *op[RW];
@@ -722,7 +722,7 @@ k_fft_zy(T *__restrict__ mesh, int ng, int ngk, int nplanes, int lag, int *__res
         olv[j] = r < ng;
         op[j] = reinterpret_cast<G *>(mesh) + plane_c * pl + (size_t) (olv[j] ? r : 0) * ngk;
       }
-      auto slot = [](int k) { return (((k >> 4) & 15) * R3 + (k >> 8)) * 16 + (k & 15); };
+      auto slot = [](int k) { return (k & 15) * ROW + (k >> 8) + R3 * ((k >> 4) & 15); };
 #pragma unroll
       for (int it = 0; it <= N / 2 / M; it++) {
         const int k = u + M * it;
