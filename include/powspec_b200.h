@@ -224,6 +224,10 @@ int psb_catalog_load(psb_context *ctx, const char *path, const psb_columns *cols
  * reference: negative redshift, no convergence up to order 32. */
 int psb_cnvt_coord(psb_context *ctx, const psb_cosmo *cosmo, double *const *arrays_dev,
     const size_t *counts, int narrays, int *order);
+/* the Legendre-Gauss order that conversion chooses for redshifts in [zmin, zmax]
+ * (src/cnvt_coord.c:356-396 on 128 samples, :277-278); host only; -1 if none of 4..32
+ * converges to cosmo->ecdst */
+int psb_cnvt_order(const psb_cosmo *cosmo, double zmin, double zmax);
 
 /* One in-place forward pass (sign -1, unnormalised: the convention of the FFTW
  * r2c plan of src/genr_mesh.c:738-743 along one axis) of the hand-written

@@ -138,6 +138,7 @@ def load_library():
                                    C.POINTER(C.c_void_p), C.POINTER(_CatalogSums)]
     L.psb_cnvt_coord.argtypes = [C.c_void_p, C.POINTER(_Cosmo), C.c_void_p, C.c_void_p, C.c_int,
                                  C.POINTER(C.c_int)]
+    L.psb_cnvt_order.argtypes = [C.POINTER(_Cosmo), C.c_double, C.c_double]
     L.psb_fft_axis.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     _lib = L
     return L

@@ -2034,6 +2034,15 @@ int psb_catalog_load(psb_context *c, const char *path, const psb_columns *cols, 
   return 0;
 }
 
+// host-only part of the integration mode: the order cnvt_coord would choose
+int psb_cnvt_order(const psb_cosmo *cm, double zmin, double zmax) {
+  if (!cm || zmin < 0 || zmin > zmax) { set_error("invalid redshift value in the catalogs\n"); return -1; }
+  const double widx = (cm->eos_w == -1) ? 0 : 3 * (1 + cm->eos_w);
+  const int order = legauss_order(cm->omega_m, cm->omega_l, cm->omega_k, widx, cm->ecdst, zmin, zmax, 128);
+  if (order == INT_MAX) { set_error("failed to perform the convergency test for integrations\n"); return -1; }
+  return order;
+}
+
 int psb_cnvt_coord(psb_context *c, const psb_cosmo *cosmo, double *const *arrays_dev,
     const size_t *counts, int narrays, int *order) {
   if (!c) { set_error("no device context\n"); return -1; }

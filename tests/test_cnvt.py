@@ -62,6 +62,33 @@ def test_port_cnvt_rejects_negative_redshift():
         port_cnvt([a], **CNVT_CASES[0]["cosmo"])
 
 
+def test_library_order_selection_matches_oracle_on_cpu():
+    """The host-side order selection of the product library (no GPU needed) against the
+    reference-pinned restatement over a grid of cosmologies, error bounds and ranges."""
+    import ctypes as C
+
+    from oracle.oracle import port_cnvt
+    from powspec_b200.api import Conf, load_library
+    L = load_library()
+    rng = np.random.default_rng(0)
+    seen = set()
+    for om, ok, w in ((0.31, 0.0, -1.0), (0.25, 0.05, -1.0), (0.3, 0.0, -0.8), (0.35, -0.02, -1.1)):
+        for err in (1e-4, 1e-6, 1e-8, 1e-10):
+            for zlo, zhi in ((0.0, 0.2), (0.4, 1.1), (0.8, 3.0), (0.5, 0.5)):
+                conf = Conf(cnvt=True, omega_m=om, omega_l=1 - om - ok, omega_k=ok, eos_w=w, ecdst=err)
+                cosmo, _ = conf._cosmo()
+                got = L.psb_cnvt_order(C.byref(cosmo), zlo, zhi)
+                a = np.zeros((64, 4))
+                a[:, 2] = np.r_[zlo, zhi, rng.uniform(zlo, zhi, 62)]
+                _, want = port_cnvt([a], omega_m=om, omega_l=1 - om - ok, omega_k=ok, eos_w=w, ecdst=err)
+                assert got == want, (om, ok, w, err, zlo, zhi, got, want)
+                seen.add(got)
+    assert len(seen) >= 4           # the grid exercises several orders
+    conf = Conf(cnvt=True, ecdst=1e-8)
+    cosmo, _ = conf._cosmo()
+    assert L.psb_cnvt_order(C.byref(cosmo), -0.1, 1.0) == -1
+
+
 # ------------------------------------------------------------------ GPU
 @pytest.fixture(scope="module")
 def ctx():
