@@ -1,0 +1,61 @@
+"""Seeded random simulation-box configurations for the parity tests: every scheme,
+interlacing on/off, even and odd mesh sizes, any subset of the multipoles 0..6,
+arbitrary unit line of sight, cubic and non-cubic boxes, linear and logarithmic
+bins with and without KMIN / KMAX, weighted and unweighted particles, auto and
+cross spectra.  The same cases are run (a) on CPU: restatement against the
+unmodified reference library, (b) on the GPU: CUDA path against the restatement.
+
+Only values the reference's own configuration check accepts are drawn
+(src/load_conf.c:990-1003: LINE_OF_SIGHT is a unit vector; :1352-1355: KMIN / KMAX
+are handed over as log10 for logarithmic bins)."""
+import numpy as np
+
+NCASES = 24
+SCHEMES = ("NGP", "CIC", "TSC", "PCS")
+
+
+def fuzz_case(seed):
+    """-> (list of catalogues, keyword arguments of oracle.run / powspec_b200.run)"""
+    r = np.random.default_rng(1000 + seed)
+    ng = int(r.integers(9, 41))
+    cubic = r.random() < 0.6
+    box = float(r.uniform(80, 400))
+    bsize = (box,) * 3 if cubic else tuple(float(box * f) for f in r.uniform(0.8, 1.3, 3))
+    ncat = 2 if r.random() < 0.3 else 1
+    cats = []
+    for _ in range(ncat):
+        n = int(r.integers(300, 4000))
+        xyz = r.random((n, 3)) * np.asarray(bsize)
+        # some particles on / next to the faces and cell boundaries (periodic wraps)
+        m = min(n, 12)
+        cells = r.integers(0, ng, (m, 3)) + r.choice([0.0, 0.5, 1 - 1e-12, 1e-12], (m, 3))
+        xyz[:m] = np.minimum(cells / ng, 1 - 1e-15) * np.asarray(bsize)
+        w = r.uniform(0.2, 2.0, n) if r.random() < 0.5 else np.ones(n)
+        cats.append(np.ascontiguousarray(np.c_[xyz, w]))
+    npole = int(r.integers(1, 8))
+    poles = tuple(sorted(int(p) for p in r.choice(7, npole, replace=False)))
+    if r.random() < 0.5:
+        los = [(1.0, 0.0, 0.0), (0.0, 1.0, 0.0), (0.0, 0.0, 1.0)][int(r.integers(3))]
+    else:
+        v = r.normal(size=3)
+        v /= np.sqrt((v * v).sum())
+        los = tuple(float(x) for x in v)
+    kf = 2 * np.pi / max(bsize)                     # fundamental of the longest side
+    kny = np.pi * ng / max(bsize)
+    kw = dict(ng=ng, assign=SCHEMES[int(r.integers(4))], interlace=bool(r.random() < 0.5),
+              poles=poles, box=bsize if not cubic else box, los=los)
+    if r.random() < 0.25:
+        kmin = float(r.uniform(0.5, 2.0) * kf)
+        kmax = float(r.uniform(0.5, 0.95) * kny)
+        kw.update(logscale=True, kmin=float(np.log10(kmin)), kmax=float(np.log10(kmax)),
+                  kbin=float(r.uniform(0.05, 0.15)))
+    else:
+        kw.update(kbin=float(r.uniform(1.0, 4.0) * kf))
+        if r.random() < 0.4:
+            kw.update(kmin=float(r.uniform(0.0, 2.0) * kf))
+        if r.random() < 0.4:
+            kw.update(kmax=float(r.uniform(0.5, 1.2) * kny))
+    if ncat == 2:
+        which = int(r.integers(3))
+        kw.update(isauto=[[True, True], [True, False], [False, False]][which], iscross=True)
+    return cats, kw

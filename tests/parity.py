@@ -23,9 +23,11 @@ def rel_err(got, want, floor=0.0):
     return float(np.max(np.abs(got - want) / scale))
 
 
-def assert_spectra_close(got, want, tol, what=""):
+def assert_spectra_close(got, want, tol, what="", abs_floor=0.0):
     """got/want: objects with nbin, cnt, k, km, kedge, lcnt, pl (list), xpl, shot.
-    `want` may be a golden dict."""
+    `want` may be a golden dict.  abs_floor: an absolute scale below which
+    differences do not count — for spectra that hold ONLY odd multipoles of a
+    periodic box, whose own maximum is rounding noise (see noise_floor)."""
     if isinstance(want, dict):
         w = want
     else:
@@ -50,7 +52,7 @@ def assert_spectra_close(got, want, tol, what=""):
             continue
         wp = np.asarray(wp)
         assert got.pl[i] is not None, what
-        floor = np.max(np.abs(wp))
+        floor = max(np.max(np.abs(wp)), abs_floor * 1e3)
         for l in range(wp.shape[0]):
             e = rel_err(got.pl[i][l], wp[l], floor * 1e-3)
             worst = max(worst, e)
@@ -58,7 +60,7 @@ def assert_spectra_close(got, want, tol, what=""):
     if w["xpl"] is not None:
         wx = np.asarray(w["xpl"])
         assert got.xpl is not None, what
-        floor = np.max(np.abs(wx))
+        floor = max(np.max(np.abs(wx)), abs_floor * 1e3)
         for l in range(wx.shape[0]):
             e = rel_err(got.xpl[l], wx[l], floor * 1e-3)
             worst = max(worst, e)
@@ -66,3 +68,15 @@ def assert_spectra_close(got, want, tol, what=""):
     else:
         assert got.xpl is None, what
     return worst
+
+
+def noise_floor(want, poles):
+    """abs_floor for assert_spectra_close: 0 unless every requested multipole is odd
+    (simulation boxes).  Then all of P_l is the rounding residue of cancelling
+    +mu / -mu pairs (~1e-16 of the shot noise, quirk Q6) and has no scale of its
+    own: differences are measured against 1e-3 of the shot-noise level instead,
+    the scale P_0 would have."""
+    if any(p % 2 == 0 for p in poles):
+        return 0.0
+    shot = [s for s in np.asarray(want.shot, dtype=np.float64) if s > 0]
+    return 1e-3 * float(np.sqrt(np.prod(shot)) if len(shot) == 2 else shot[0]) if shot else 0.0

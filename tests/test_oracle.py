@@ -149,3 +149,18 @@ def test_cpu_fft_against_numpy(port_oracle):
         back = np.zeros(shape)
         lib.fftcpu_d_c2r_3d(p, out.ctypes.data, back.ctypes.data)
         assert np.abs(back / a.size - a).max() < 1e-12
+
+
+@pytest.mark.parametrize("seed", range(__import__("tests.fuzz_cases", fromlist=["NCASES"]).NCASES))
+def test_port_matches_reference_on_random_configurations(seed, port_oracle, ref_oracle):
+    """Seeded random simulation-box configurations (tests/fuzz_cases.py): the
+    restatement against the unmodified reference — what licenses the restatement as
+    the checker of the same cases on the GPU (tests/test_gpu_fuzz.py)."""
+    from tests.fuzz_cases import fuzz_case
+    cats, kw = fuzz_case(seed)
+    data = cats if len(cats) > 1 else cats[0]
+    want = ref_oracle.run(data, **kw)
+    got = port_oracle.run(data, **kw)
+    assert want.nbin > 0
+    from tests.parity import noise_floor
+    assert_spectra_close(got, want, 1e-10, f"fuzz {seed}: {kw}", abs_floor=noise_floor(want, kw["poles"]))
