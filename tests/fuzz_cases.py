@@ -59,3 +59,61 @@ def fuzz_case(seed):
         which = int(r.integers(3))
         kw.update(isauto=[[True, True], [True, False], [False, False]][which], iscross=True)
     return cats, kw
+
+
+NSURVEY = 12
+
+
+def survey_case(seed):
+    """Survey-like configuration: data + randoms in a wedge of sky (already comoving
+    Cartesian), completeness and FKP weights, automatic box with padding or a given
+    one, any scheme, interlacing, any subset of the multipoles, one or two catalogues.
+    -> (data list, keyword arguments incl. rand= and scalars=)"""
+    from oracle.oracle import survey_scalars
+    r = np.random.default_rng(5000 + seed)
+    ncat = 2 if r.random() < 0.35 else 1
+    ra0, dec0 = r.uniform(0, 300), r.uniform(-40, 20)
+    dra, ddec = r.uniform(30, 60), r.uniform(20, 50)
+    d0, d1 = r.uniform(500, 900), r.uniform(1200, 1800)
+
+    def cat(n):
+        ra = np.deg2rad(r.uniform(ra0, ra0 + dra, n))
+        dec = np.deg2rad(r.uniform(dec0, dec0 + ddec, n))
+        dist = r.uniform(d0, d1, n)
+        nz = r.uniform(1e-4, 5e-4, n)
+        wfkp = 1 / (1 + 1e4 * nz)
+        wc = r.uniform(0.7, 1.3, n)
+        xyz = dist[:, None] * np.c_[np.cos(dec) * np.cos(ra), np.cos(dec) * np.sin(ra), np.sin(dec)]
+        return np.ascontiguousarray(np.c_[xyz, wc * wfkp]), wc, wfkp, nz
+
+    data, rand, scalars = [], [], []
+    for _ in range(ncat):
+        d, dwc, dwf, dnz = cat(int(r.integers(800, 3000)))
+        q, qwc, qwf, qnz = cat(int(r.integers(5000, 12000)))
+        data.append(d); rand.append(q)
+        scalars.append(survey_scalars(dwc, dwf, dnz, qwc, qwf, qnz))
+    npole = int(r.integers(1, 6))
+    poles = tuple(sorted(int(p) for p in r.choice(7, npole, replace=False)))
+    if r.random() < 0.8 and 0 not in poles:
+        poles = (0,) + poles[1:] if len(poles) > 1 else (0,)
+    ext = np.ptp(np.vstack(data + rand)[:, :3], axis=0)
+    kw = dict(ng=int(r.integers(12, 29)), assign=SCHEMES[int(r.integers(4))],
+              interlace=bool(r.random() < 0.5), poles=poles, issim=False, rand=rand, scalars=scalars)
+    if r.random() < 0.3:
+        kw["box"] = tuple(float(np.ceil(e * f)) for e, f in zip(ext, r.uniform(1.05, 1.4, 3)))
+    else:
+        kw["bpad"] = tuple(float(x) for x in r.uniform(0.0, 0.1, 3))
+    side = max(kw["box"]) if "box" in kw else float(ext.max()) * 1.1
+    kf = 2 * np.pi / side
+    if r.random() < 0.25:
+        kw.update(logscale=True, kmin=float(np.log10(r.uniform(0.8, 2.0) * kf)),
+                  kbin=float(r.uniform(0.06, 0.15)))
+    else:
+        kw.update(kbin=float(r.uniform(1.0, 3.0) * kf))
+        if r.random() < 0.4:
+            kw.update(kmin=float(r.uniform(0.0, 1.5) * kf))
+        if r.random() < 0.4:
+            kw.update(kmax=float(r.uniform(0.5, 1.1) * np.pi * kw["ng"] / side))
+    if ncat == 2:
+        kw.update(isauto=[[True, True], [True, False], [False, False]][int(r.integers(3))], iscross=True)
+    return data, kw

@@ -164,3 +164,22 @@ def test_port_matches_reference_on_random_configurations(seed, port_oracle, ref_
     assert want.nbin > 0
     from tests.parity import noise_floor
     assert_spectra_close(got, want, 1e-10, f"fuzz {seed}: {kw}", abs_floor=noise_floor(want, kw["poles"]))
+
+
+@pytest.mark.parametrize("seed", range(__import__("tests.fuzz_cases", fromlist=["NSURVEY"]).NSURVEY))
+def test_port_matches_reference_on_random_surveys(seed, port_oracle, ref_oracle):
+    """Seeded random survey configurations (data + randoms, FKP weights, automatic or
+    given box, any scheme / interlacing / multipoles, auto and cross).  The reference
+    runs on one thread (data race in its get_coord_bound, see above)."""
+    from tests.fuzz_cases import survey_case
+    data, kw = survey_case(seed)
+    data = data if len(data) > 1 else data[0]
+    gomp = C.CDLL("libgomp.so.1")
+    gomp.omp_set_num_threads(1)
+    try:
+        want = ref_oracle.run(data, **kw)
+    finally:
+        gomp.omp_set_num_threads(4)
+    got = port_oracle.run(data, **kw)
+    assert want.nbin > 0
+    assert_spectra_close(got, want, 1e-9, f"survey fuzz {seed}")
