@@ -63,3 +63,40 @@ def test_emulated_slabs_cross_and_single_precision(ctx, port_oracle):
                 for sa, sb in zip(np.array_split(a, 2), np.array_split(b, 2))]
         got = slab_power_emulated(engines, cats, [float(a[:, 3].sum()), float(b[:, 3].sum())])
         assert_spectra_close(got, want, tol, f"slab cross prec={prec}")
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_emulated_slabs_on_random_configurations(seed, ctx, port_oracle):
+    """The seeded random box configurations of tests/fuzz_cases.py through the slab
+    path, over the largest admissible rank count (GRID_SIZE divisible, at least 3
+    owned planes per rank): odd mesh sizes, slabs as thin as the halo, non-cubic
+    boxes, any line of sight / bins / multipoles, cross spectra."""
+    import torch
+
+    import powspec_b200 as pb
+    from powspec_b200.distributed import GpuSlabEngine, slab_power_emulated
+    from tests.fuzz_cases import fuzz_case
+    from tests.parity import noise_floor
+    cats, kw = fuzz_case(seed)
+    ng = kw["ng"]
+    ranks = [g for g in (8, 6, 5, 4, 3, 2) if ng % g == 0 and ng // g >= 3]
+    if not ranks:
+        pytest.skip(f"GRID_SIZE {ng} has no admissible slab count")
+    G = ranks[0]
+    want = port_oracle.run(cats if len(cats) > 1 else cats[0], **kw)
+    ncat = len(cats)
+    isauto = kw.get("isauto", [True] * ncat)
+    conf = pb.Conf(ndata=ncat, issim=True, bsize=tuple(np.broadcast_to(np.asarray(kw["box"], float), (3,))),
+                   gsize=ng, assign=pb.powspec_assign_names.index(kw["assign"]), intlace=kw["interlace"],
+                   poles=kw["poles"], kbin=kw["kbin"], kmin=kw.get("kmin", 0.0), kmax=kw.get("kmax", -1.0),
+                   logscale=kw.get("logscale", False), los=kw["los"],
+                   isauto=tuple(isauto) + (False,) * (2 - ncat), iscross=kw.get("iscross", False))
+    engines = [GpuSlabEngine(ctx, conf, G, r) for r in range(G)]
+    shares = [np.array_split(c, G) for c in cats]
+    per_rank = [[torch.from_numpy(np.ascontiguousarray(shares[c][r])).cuda() for c in range(ncat)]
+                for r in range(G)]
+    got = slab_power_emulated(engines, per_rank, [float(c[:, 3].sum()) for c in cats],
+                              isauto=list(isauto), iscross=kw.get("iscross", False))
+    worst = assert_spectra_close(got, want, TOL_DOUBLE, f"slab fuzz {seed} G={G}: {kw}",
+                                 abs_floor=noise_floor(want, kw["poles"]))
+    print(f"slab fuzz {seed} G={G} ng={ng}: worst rel err {worst:.2e}")
