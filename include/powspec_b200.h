@@ -166,7 +166,10 @@ int psb_timings(const psb_context *ctx, double *ms, int n);
 /* number of kernel launches (ours + cuFFT calls counted as 1) of the last run */
 long psb_launch_count(const psb_context *ctx);
 
-/* Tunables (tests / ablations): name = "sort" (0/1), "geom_cache" (0/1) ... */
+/* Tunables (tests / ablations; the list is in psb_set_option, csrc/context.cu):
+ * "sort", "strip", "coop", "own_fft", "fft_fused", "stream", "stream_chunk",
+ * "stream_taper", "h2d_threads", "survey_direct", "geom_sym" ...; returns non-zero
+ * for an unknown name */
 int psb_set_option(psb_context *ctx, const char *name, long value);
 
 const char *psb_last_error(void);
