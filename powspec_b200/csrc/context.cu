@@ -168,7 +168,10 @@ struct psb_context {
                                         // (capped at the hardware concurrency; 8 -> 16 on the 16-core
                                         // B200 host: 36 -> 44 GB/s, config 2 from malloc'd memory 121 -> 107 ms)
   long opt_stream = 1;                  // overlap H2D with assignment for host catalogues (sims)
-  long opt_stream_chunk = 1 << 24;      // particles per streamed chunk (512 MiB)
+  long opt_stream_chunk = 12500000;     // particles per streamed chunk (400 MB): the smallest whose
+                                        // sort + scatter (~6 ms, one sweep of the meshes) still keeps
+                                        // up with its upload (7.2 ms); config 2 e2e 93.9 / 92.5 / 91.6 ms
+                                        // with 20 M / 16.8 M / 12.5 M
   long opt_stream_taper = 0;            // > 0: the last chunks halve down to this many particles (measured: slower)
 
   // state carried from psb_mesh to psb_power

@@ -14,17 +14,29 @@ NCASES = 24
 SCHEMES = ("NGP", "CIC", "TSC", "PCS")
 
 
-def fuzz_case(seed):
+NMEDIUM = 8
+
+
+def medium_case(seed):
+    """The same draw at sizes where the particle sort and the strip-ordered,
+    z-coalesced scatter are engaged (>= 65536 particles): meshes of 33..80 cells per
+    side (odd sizes, sizes that are not a multiple of the strip height)."""
+    cats, kw = fuzz_case(seed, ng_range=(33, 81), n_range=(70_000, 250_000), base=3000)
+    kw["interlace"] = seed % 2 == 0
+    return cats, kw
+
+
+def fuzz_case(seed, ng_range=(9, 41), n_range=(300, 4000), base=1000):
     """-> (list of catalogues, keyword arguments of oracle.run / powspec_b200.run)"""
-    r = np.random.default_rng(1000 + seed)
-    ng = int(r.integers(9, 41))
+    r = np.random.default_rng(base + seed)
+    ng = int(r.integers(*ng_range))
     cubic = r.random() < 0.6
     box = float(r.uniform(80, 400))
     bsize = (box,) * 3 if cubic else tuple(float(box * f) for f in r.uniform(0.8, 1.3, 3))
     ncat = 2 if r.random() < 0.3 else 1
     cats = []
     for _ in range(ncat):
-        n = int(r.integers(300, 4000))
+        n = int(r.integers(*n_range))
         xyz = r.random((n, 3)) * np.asarray(bsize)
         # some particles on / next to the faces and cell boundaries (periodic wraps)
         m = min(n, 12)

@@ -62,3 +62,25 @@ def test_random_survey_against_oracle(seed, ctx, port_oracle):
             ctx.set_option("survey_direct", 1)
         worst = assert_spectra_close(got, want, TOL_DOUBLE, f"survey fuzz {seed} direct={direct}")
         print(f"survey fuzz {seed} direct={direct}: worst rel err {worst:.2e}")
+
+
+@pytest.mark.parametrize("seed", range(__import__("tests.fuzz_cases", fromlist=["NMEDIUM"]).NMEDIUM))
+def test_medium_random_configuration_against_oracle(seed, ctx, port_oracle):
+    """Random box configurations with 7e4..2.5e5 particles on 33..80 cells per side:
+    the counting sort, the strip order (mesh sizes that are not a multiple of the
+    strip height, odd sizes) and the z-coalesced scatter are engaged.  The density
+    meshes are compared cell by cell as well as the spectra."""
+    import powspec_b200
+    from tests.fuzz_cases import medium_case
+    cats, kw = medium_case(seed)
+    data = cats if len(cats) > 1 else cats[0]
+    want = port_oracle.run(data, keep_mesh=True, **kw)
+    got = powspec_b200.run(data, ctx=ctx, keep_mesh=True, **kw)
+    for i in range(len(cats)):
+        scale = np.abs(want.Fr[i]).max()
+        assert np.abs(got.Fr[i] - want.Fr[i]).max() < 1e-12 * scale, f"medium fuzz {seed}: mesh {i}"
+        if kw["interlace"]:
+            assert np.abs(got.Frl[i] - want.Frl[i]).max() < 1e-12 * scale, f"medium fuzz {seed}: shifted mesh {i}"
+    worst = assert_spectra_close(got, want, TOL_DOUBLE, f"medium fuzz {seed}: {kw}",
+                                 abs_floor=noise_floor(want, kw["poles"]))
+    print(f"medium fuzz {seed}: worst rel err {worst:.2e}")

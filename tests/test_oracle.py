@@ -183,3 +183,16 @@ def test_port_matches_reference_on_random_surveys(seed, port_oracle, ref_oracle)
     got = port_oracle.run(data, **kw)
     assert want.nbin > 0
     assert_spectra_close(got, want, 1e-9, f"survey fuzz {seed}")
+
+
+@pytest.mark.parametrize("seed", range(__import__("tests.fuzz_cases", fromlist=["NMEDIUM"]).NMEDIUM))
+def test_port_matches_reference_on_medium_random_configurations(seed, port_oracle, ref_oracle):
+    """The random box configurations at sizes that engage the GPU's particle sort
+    (tests/test_gpu_fuzz.py::test_medium_random_configuration_against_oracle)."""
+    from tests.fuzz_cases import medium_case
+    from tests.parity import noise_floor
+    cats, kw = medium_case(seed)
+    data = cats if len(cats) > 1 else cats[0]
+    want = ref_oracle.run(data, **kw)
+    got = port_oracle.run(data, **kw)
+    assert_spectra_close(got, want, 1e-10, f"medium fuzz {seed}: {kw}", abs_floor=noise_floor(want, kw["poles"]))
