@@ -10,3 +10,4 @@ from .api import (  # noqa: F401
     Conf, Cata, Mesh, PK, PowspecB200Error, Context, genr_mesh, powspec, mesh_destroy,
     powspec_destroy, powspec_assign_names, load_library, library_path, run,
 )
+from .save_res import save_res  # noqa: F401

@@ -171,6 +171,10 @@ class Conf:
     isauto: tuple = (True, False)
     iscross: bool = False
     verbose: bool = False
+    # outputs, read by save_res() (src/save_res.c:35-229)
+    oauto: tuple | None = None      # OUTPUT_AUTO: one file name per catalogue
+    ocross: str | None = None       # OUTPUT_CROSS
+    oheader: bool = True            # OUTPUT_HEADER (DEFAULT_HEADER, src/define.h:62)
     # coordinate conversion, read by cnvt_coord() (src/cnvt_coord.c:549-582)
     cnvt: bool = False              # any of DATA_CONVERT / RAND_CONVERT set
     dcnvt: tuple = (False, False)   # DATA_CONVERT per catalogue
