@@ -249,6 +249,21 @@ void trace_mark(const char *what) {
 }
 
 void collect_timings(psb_context *c) {
+  // PSB_TRACE: device-side timeline of every stage interval of the run (all streams),
+  // in ms since the first one started
+  static const bool trace = getenv("PSB_TRACE") != nullptr;
+  if (trace && !c->intervals.empty()) {
+    static const char *names[PSB_T_COUNT] = {"h2d", "bounds", "sort", "memset", "assign", "fft",
+        "geom", "bin", "ylm", "fft_strided", "cnvt", "total"};
+    cudaEvent_t origin = c->intervals[0].a;
+    for (auto &iv : c->intervals) {
+      float t0 = 0, t1 = 0;
+      if (cudaEventElapsedTime(&t0, origin, iv.a) == cudaSuccess &&
+          cudaEventElapsedTime(&t1, origin, iv.b) == cudaSuccess)
+        fprintf(stderr, "[psb-trace]   device %-11s %9.3f -> %9.3f ms\n", names[iv.stage], t0, t1);
+    }
+    cudaGetLastError();
+  }
   for (auto &iv : c->intervals) {
     float t = 0;
     if (cudaEventElapsedTime(&t, iv.a, iv.b) == cudaSuccess) c->ms[iv.stage] += t;
