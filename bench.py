@@ -345,7 +345,7 @@ def main():
         host = torch.empty((n, 4), dtype=torch.float64, pin_memory=True)
         ctx.L.psb_copy_to_host(ctx.h, host.data_ptr(), cat_dev[0], n * 32)
         cata_host = Cata(data=[host], wdata=[float(n)])
-        ms_e2e, _, stages_e2e, _, pk_e = timed(cata_host, args.steps, 1)
+        ms_e2e, _, stages_e2e, _, pk_e = timed(cata_host, args.steps, max(args.warmup, 3))
         ms_e2e_step = ms_e2e / args.steps
         d2h = (2 + 4 * pk_e.nl) * pk_e.nbin * 8 + 6 * 8 * 148 * 8
         e2e = {"value": world * n / (ms_e2e_step * 1e-3), "unit": "particles/s",
