@@ -6,8 +6,6 @@ driving the library from Python writes files a consumer of the reference's
 outputs cannot tell apart.  The C host keeps using its own `save_res`."""
 from __future__ import annotations
 
-import os
-
 import numpy as np
 
 from .api import Cata, Conf, Mesh, PK, PowspecB200Error, powspec_assign_names
