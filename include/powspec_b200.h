@@ -204,6 +204,58 @@ int psb_slab_bin(psb_context *ctx, const psb_params *par, const psb_slab *slab,
 psb_result *psb_slab_finish(psb_context *ctx, const psb_params *par, const double *pl0,
     const double *pl1, const double *xpl, const double wdata[2]);
 
+/* ---------------------------------------------------------------------------
+ * The slab decomposition driven from inside the library (csrc/dist.cu): the exchanges
+ * are issued by the library itself, stream-ordered, over one of two transports.
+ *
+ *  - psb_dist: ONE rank.  One process per GPU (bench.py under torchrun): rank 0 calls
+ *    psb_dist_unique_id, the host distributes the 128 bytes, every rank calls
+ *    psb_dist_create_nccl (libnccl.so.2 is dlopen'ed: the copy the host process has
+ *    already loaded, else POWSPEC_B200_NCCL, else the loader path).
+ *  - psb_group: ALL ranks in one process, one host thread per rank, exchanges by peer
+ *    copies (no NCCL).  This is what the reference's single-process C host gets through
+ *    genr_mesh()/powspec() with POWSPEC_B200_DEVICES=0,1,...; a device may be listed
+ *    more than once (virtual ranks, tests).
+ *
+ * begin / add / finish are collective: every rank makes the same calls.  Simulation
+ * boxes only.  Where the ranks can map each other's memory (same process, or CUDA IPC),
+ * the y pass of the FFT stores its result straight into the destination ranks' buffers
+ * (FFT + transpose in one kernel, no all-to-all); POWSPEC_B200_P2P=0 or option "p2p"
+ * forces the all-to-all path. */
+typedef struct psb_dist psb_dist;
+typedef struct psb_group psb_group;
+int psb_dist_unique_id(void *id128);
+psb_dist *psb_dist_create_nccl(psb_context *ctx, int nranks, int rank, const void *id128);
+void psb_dist_destroy(psb_dist *d);
+int psb_dist_set_option(psb_dist *d, const char *name, long value);
+int psb_dist_begin(psb_dist *d, const psb_params *par);
+/* one chunk of THIS rank's share of catalogue `cat`: device memory, any distribution */
+int psb_dist_add(psb_dist *d, int cat, const double *particles_dev, size_t n);
+/* wdata: global sum of weights per catalogue; every rank gets the same result */
+psb_result *psb_dist_finish(psb_dist *d, const double wdata[2]);
+/* CUDA-event stage times of the last run on this rank, ms */
+enum {
+  PSB_D_ROUTE = 0, PSB_D_ASSIGN, PSB_D_HALO, PSB_D_FFT_ZY, PSB_D_TRANSPOSE, PSB_D_FFT_X, PSB_D_BIN,
+  PSB_D_REDUCE, PSB_D_COUNT
+};
+int psb_dist_timings(const psb_dist *d, double *ms, int n);
+/* [0] transpose bytes this rank sent, [1] particle bytes it routed away, [2] 1 if the
+ * transposes were peer stores fused into the y pass */
+int psb_dist_traffic(const psb_dist *d, double *out, int n);
+const char *psb_dist_transport(const psb_dist *d);
+psb_context *psb_dist_context(psb_dist *d);
+
+psb_group *psb_group_create(const int *devices, int nranks);
+void psb_group_destroy(psb_group *g);
+int psb_group_size(const psb_group *g);
+psb_dist *psb_group_rank(psb_group *g, int r);
+int psb_group_set_option(psb_group *g, const char *name, long value);
+/* genr_mesh() / powspec() over the group: rank r takes the r-th contiguous share of
+ * every catalogue (host memory, or device memory of one GPU) */
+int psb_group_mesh(psb_group *g, const psb_params *par, const psb_cats *cats);
+psb_result *psb_group_power(psb_group *g, const psb_params *par);
+psb_result *psb_group_run(psb_group *g, const psb_params *par, const psb_cats *cats);
+
 /* Binary catalogue ingest (the step before the boundary): a
  * NumPy .npy file — 2-D, C order, little-endian float64 or float32, shape
  * (N, ncols) — is streamed from the page cache to the device and turned into the

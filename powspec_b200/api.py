@@ -140,6 +140,34 @@ def load_library():
                                  C.POINTER(C.c_int)]
     L.psb_cnvt_order.argtypes = [C.POINTER(_Cosmo), C.c_double, C.c_double]
     L.psb_fft_axis.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    vp = C.c_void_p
+    L.psb_dist_unique_id.argtypes = [vp]
+    L.psb_dist_create_nccl.restype = vp
+    L.psb_dist_create_nccl.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.psb_dist_destroy.argtypes = [vp]
+    L.psb_dist_set_option.argtypes = [vp, C.c_char_p, C.c_long]
+    L.psb_dist_begin.argtypes = [vp, C.POINTER(_Params)]
+    L.psb_dist_add.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.psb_dist_finish.restype = vp
+    L.psb_dist_finish.argtypes = [vp, C.POINTER(C.c_double)]
+    L.psb_dist_timings.argtypes = [vp, vp, C.c_int]
+    L.psb_dist_traffic.argtypes = [vp, vp, C.c_int]
+    L.psb_dist_transport.restype = C.c_char_p
+    L.psb_dist_transport.argtypes = [vp]
+    L.psb_dist_context.restype = vp
+    L.psb_dist_context.argtypes = [vp]
+    L.psb_group_create.restype = vp
+    L.psb_group_create.argtypes = [C.POINTER(C.c_int), C.c_int]
+    L.psb_group_destroy.argtypes = [vp]
+    L.psb_group_size.argtypes = [vp]
+    L.psb_group_rank.restype = vp
+    L.psb_group_rank.argtypes = [vp, C.c_int]
+    L.psb_group_set_option.argtypes = [vp, C.c_char_p, C.c_long]
+    L.psb_group_mesh.argtypes = [vp, C.POINTER(_Params), C.POINTER(_Cats)]
+    L.psb_group_power.restype = vp
+    L.psb_group_power.argtypes = [vp, C.POINTER(_Params)]
+    L.psb_group_run.restype = vp
+    L.psb_group_run.argtypes = [vp, C.POINTER(_Params), C.POINTER(_Cats)]
     _lib = L
     return L
 
@@ -283,6 +311,26 @@ class PK:
     launches: int = 0
 
 
+def pk_from_result(L, r, conf) -> "PK":
+    """Copy a psb_result into the host-side PK (the caller frees r)."""
+    nbin, nl = L.psb_result_nbin(r), L.psb_result_nl(r)
+
+    def get(what, n, dtype=np.float64, idx=0):
+        a = np.empty(n, dtype=dtype)
+        return a if L.psb_result_get(r, what, idx, a.ctypes.data) >= 0 else None
+
+    pl = []
+    for i in range(2):
+        q = get(GET_PL, nl * nbin, idx=i)
+        pl.append(None if q is None else q.reshape(nl, nbin))
+    x = get(GET_XPL, nl * nbin)
+    return PK(nl=nl, nbin=nbin, poles=list(conf.poles), k=get(GET_K, nbin),
+              kedge=get(GET_KEDGE, nbin + 1), km=get(GET_KM, nbin),
+              cnt=get(GET_CNT, nbin, np.uint64), lcnt=get(GET_LCNT, nl * nbin).reshape(nl, nbin),
+              pl=pl, xpl=None if x is None else x.reshape(nl, nbin),
+              shot=get(GET_SHOT, 2), norm=get(GET_NORM, 2))
+
+
 def _ptr_of(arr):
     """(pointer, n, memspace, keepalive) of one particle array."""
     if arr is None:
@@ -382,25 +430,9 @@ class Context:
         if not r:
             raise _err(self.L, "powspec", POWSPEC_ERR_PK)
         try:
-            L = self.L
-            nbin, nl = L.psb_result_nbin(r), L.psb_result_nl(r)
-
-            def get(what, n, dtype=np.float64, idx=0):
-                a = np.empty(n, dtype=dtype)
-                return a if L.psb_result_get(r, what, idx, a.ctypes.data) >= 0 else None
-
-            pl = []
-            for i in range(2):
-                q = get(GET_PL, nl * nbin, idx=i)
-                pl.append(None if q is None else q.reshape(nl, nbin))
-            x = get(GET_XPL, nl * nbin)
-            pk = PK(nl=nl, nbin=nbin, poles=list(conf.poles), k=get(GET_K, nbin),
-                    kedge=get(GET_KEDGE, nbin + 1), km=get(GET_KM, nbin),
-                    cnt=get(GET_CNT, nbin, np.uint64), lcnt=get(GET_LCNT, nl * nbin).reshape(nl, nbin),
-                    pl=pl, xpl=None if x is None else x.reshape(nl, nbin),
-                    shot=get(GET_SHOT, 2), norm=get(GET_NORM, 2))
+            pk = pk_from_result(self.L, r, conf)
             pk.timings_ms = self.timings()
-            pk.launches = int(L.psb_launch_count(self.h))
+            pk.launches = int(self.L.psb_launch_count(self.h))
             return pk
         finally:
             self.L.psb_result_free(r)

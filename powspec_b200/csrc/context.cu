@@ -15,10 +15,8 @@
 //   dens_k0, powspec, count_mode  src/multipole.c:435-505, 1179-1278, 1044-1162
 //                                                               -> psb_power()
 
-#include "psb_internal.h"
-#include "../../include/powspec_b200.h"
+#include "psb_context.h"
 
-#include <cufft.h>
 #include <unistd.h>
 #include <sys/stat.h>
 #include <sys/mman.h>
@@ -57,6 +55,7 @@ struct QuietErrors {
   ~QuietErrors() { g_quiet = false; }
 };
 const char *get_error() { return g_err; }
+void errors_quiet(bool on) { g_quiet = on; }
 
 static const double PI = 0x1.921fb54442d18p+1;  // src/define.h:37
 
@@ -70,143 +69,12 @@ static const double PI = 0x1.921fb54442d18p+1;  // src/define.h:37
     }                                                                           \
   } while (0)
 
-// ---------------------------------------------------------------------------
-// growable device buffer
-// ---------------------------------------------------------------------------
-struct DevBuf {
-  void *p = nullptr;
-  size_t cap = 0;
-  int reserve(size_t bytes) {
-    if (bytes <= cap) return 0;
-    if (p) cudaFree(p);
-    p = nullptr; cap = 0;
-    cudaError_t e = cudaMalloc(&p, bytes);
-    if (e != cudaSuccess) {
-      set_error("failed to allocate %.3f GB of device memory: %s\n", bytes / 1e9,
-          cudaGetErrorString(e));
-      cudaGetLastError();
-      return -1;
-    }
-    cap = bytes;
-    return 0;
-  }
-  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-  template <typename T> T *as() const { return static_cast<T *>(p); }
-};
-
-struct Interval { int stage; cudaEvent_t a, b; };
-
 }  // namespace psb
 
 using namespace psb;
 
-// ---------------------------------------------------------------------------
-// the context
-// ---------------------------------------------------------------------------
-struct psb_context {
-  int device = 0;
-  int sms = 148;
-  cudaStream_t st = nullptr;            // compute
-  cudaStream_t st_geom = nullptr;       // data-independent mode counting
-  cudaEvent_t ev_geom = nullptr;
-  cudaStream_t st_aux = nullptr;        // mesh memsets, overlapped with the particle sort
-  cudaEvent_t ev_aux_go = nullptr, ev_aux_done = nullptr, ev_memset[2] = {nullptr, nullptr};
-  cudaEvent_t memset_pending = nullptr; // the scatter must wait for this memset first
+namespace psb_host {
 
-  // particles
-  DevBuf part_in[2][2];                 // [cat][data|rand] staged copies of host arrays
-  DevBuf chunkbuf[2];                   // double-buffered device chunks of a streamed catalogue
-  cudaStream_t st_copy = nullptr;       // H2D engine stream of the streaming path
-  cudaEvent_t ev_filled[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
-  DevBuf sorted, keys, hist, cursor, cubtmp, bounds_part;
-  size_t bounds_used = 0;               // bytes of bounds_part holding deferred bounds partials
-  void *pinned[2] = {nullptr, nullptr};
-  size_t pinned_bytes = 0;
-  cudaEvent_t pinned_free[2] = {nullptr, nullptr};
-
-  // meshes: [cat][field]; survey extras
-  DevBuf mesh[2][2];
-  DevBuf fkl[2], fka, fk0copy[2];
-
-  // FFT
-  cufftHandle plan_fwd = 0, plan_inv = 0, plan_z = 0, plan_z2 = 0, plan_x = 0;
-  bool have_z = false, have_z2 = false, have_x = false;
-  bool own_fft = false;                 // y/x passes by k_fft_strided (fft_strided.cu)
-  double fft_k2max = 0;                 // last bin edge in k^2 (tile skipping of the x pass)
-  int plan_ng = 0, plan_prec = 0, plan_zp = 0;
-  bool have_fwd = false, have_inv = false;
-  DevBuf fftwork, fftdone, cnvt_tab;
-
-  // slab-decomposed FFT plans
-  cufftHandle slab_yz = 0, slab_x = 0;
-  int slab_ng = 0, slab_nx = 0, slab_prec = 0, slab_zp = 1;
-  bool slab_have = false, slab_own = false, slab_own_x = false, slab_own_z = false;
-  bool slab_has_yz = false, slab_has_x = false;
-
-  // tables and bins
-  DevBuf tables, binscratch, bins;
-  std::vector<double> host_tables;
-
-  // options
-  long opt_sort = 1;
-  long opt_sort_min = 1 << 16;
-  long opt_geom_sym = 1;                // fold +-n_x, +-n_y in the mode-counting pass
-  long opt_coop = 1;                    // z-coalesced scatter kernel
-  long opt_coop_variant = 0;
-  long opt_survey_direct = 1;           // survey l > 0: bin Fk0 x Fka_m directly (no Fkl field)
-  long opt_fft_skip = 1;                // x pass skips the columns beyond the last bin edge
-  long opt_fft_l2_mb = 0;               // L2 budget of a z + y plane group (0: whole mesh at once)
-  long opt_fft_streams = 1;             // 2: alternate the plane groups between two streams
-  long opt_fft_fused = 0;               // z + y passes in one persistent kernel (L2 hand-over)
-  long opt_fft_own_z = -1;              // hand-written r2c z pass: 1 / 0 (cuFFT batched 1-D) / -1 auto
-  long opt_fft_own_x = -1;              // hand-written x pass: 1 / 0 (cuFFT strided batched 1-D) / -1 auto
-  long opt_memset_overlap = 0;          // mesh memsets on a side stream, under the particle sort
-  long opt_own_fft = 1;                 // hand-written strided FFT passes where available
-  long opt_xgroup = 0;                  // > 0: coarse bucket sort (planes per bucket)
-  long opt_strip = 64;                  // rows per strip of the sort order
-  long opt_h2d_threads = 16;            // host threads staging pageable memory into pinned buffers
-                                        // (capped at the hardware concurrency; 8 -> 16 on the 16-core
-                                        // B200 host: 36 -> 44 GB/s, config 2 from malloc'd memory 121 -> 107 ms)
-  long opt_stream = 1;                  // overlap H2D with assignment for host catalogues (sims)
-  long opt_stream_chunk = 12500000;     // particles per streamed chunk (400 MB): the smallest whose
-                                        // sort + scatter (~6 ms, one sweep of the meshes) still keeps
-                                        // up with its upload (7.2 ms); config 2 e2e 93.9 / 92.5 / 91.6 ms
-                                        // with 20 M / 16.8 M / 12.5 M
-  long opt_stream_taper = 0;            // > 0: the last chunks halve down to this many particles (measured: slower)
-
-  // state carried from psb_mesh to psb_power
-  bool mesh_ready = false;
-  psb_params par;
-  double bmin[3], bsize[3], bmax[3];
-  double shot[2], norm[2];
-
-  // k-bins, per-axis tables and mode counts prepared ahead of the FFTs
-  bool bins_ready = false;
-  psb_params bins_par;
-  double bins_box[3];
-  int nbin = 0;
-  std::vector<double> kedge;
-  BinGeom bg;
-  size_t bin_sb = 0;
-
-  // timings
-  std::vector<Interval> intervals;
-  std::vector<cudaEvent_t> evpool;
-  double ms[PSB_T_COUNT];
-  double host_h2d_ms = 0;
-  long launches = 0;
-};
-
-struct psb_result {
-  int nbin = 0, nl = 0;
-  std::vector<double> k, kedge, km, lcnt, pl[2], xpl;
-  std::vector<unsigned long long> cnt;
-  bool has_pl[2] = {false, false}, has_xpl = false;
-  double shot[2] = {0, 0}, norm[2] = {0, 0};
-  double bmin[3], bsize[3], bmax[3];
-};
-
-namespace {
 
 cudaEvent_t get_event(psb_context *c) {
   cudaEvent_t e;
@@ -215,18 +83,6 @@ cudaEvent_t get_event(psb_context *c) {
   return e;
 }
 
-struct StageScope {
-  psb_context *c; int stage; cudaStream_t s; cudaEvent_t a;
-  StageScope(psb_context *c_, int stage_, cudaStream_t s_) : c(c_), stage(stage_), s(s_) {
-    a = get_event(c);
-    cudaEventRecord(a, s);
-  }
-  ~StageScope() {
-    cudaEvent_t b = get_event(c);
-    cudaEventRecord(b, s);
-    c->intervals.push_back({stage, a, b});
-  }
-};
 
 void reset_timings(psb_context *c) {
   for (auto &iv : c->intervals) { c->evpool.push_back(iv.a); c->evpool.push_back(iv.b); }
@@ -431,7 +287,7 @@ int sort_assign_chunk(psb_context *c, const double *src, size_t len, const Assig
   double *partials = nullptr;
   if (bounds) {
     const int nblk = do_sort ? row_keys_blocks(len) : c->sms * 8;
-    if (c->bounds_part.reserve(c->bounds_used + sizeof(double) * 6 * nblk)) return -1;
+    if (c->bounds_part.reserve_keep(c->bounds_used + sizeof(double) * 6 * nblk, c->bounds_used, c->st)) return -1;
     partials = reinterpret_cast<double *>(c->bounds_part.as<char>() + c->bounds_used);
     c->bounds_used += sizeof(double) * 6 * nblk;
     if (!do_sort) {
@@ -483,7 +339,7 @@ int sort_assign_chunk(psb_context *c, const double *src, size_t len, const Assig
 const size_t DEV_CHUNK = (size_t) 1 << 28;      // particles per chunk (8.6 GB of records)
 
 int assign_catalog(psb_context *c, const double *dev, size_t n, const AssignGeom &g, int scheme,
-    int precision, double wscale, void *m0, void *m1, bool bounds = false) {
+    int precision, double wscale, void *m0, void *m1, bool bounds) {
   for (size_t off = 0; off < n; off += DEV_CHUNK)
     if (sort_assign_chunk(c, dev + 4 * off, std::min(DEV_CHUNK, n - off), g, scheme, precision,
           wscale, m0, m1, nullptr, bounds))
@@ -494,7 +350,9 @@ int assign_catalog(psb_context *c, const double *dev, size_t n, const AssignGeom
 // room for the deferred bounds partials of `nchunk` chunks
 int bounds_begin(psb_context *c, size_t nchunk) {
   c->bounds_used = 0;
-  return c->bounds_part.reserve(sizeof(double) * 6 * (size_t) (c->sms * 16 + 64) * (nchunk + 1));
+  // sized from the grids the key pass really launches (row_keys_blocks does not depend on
+  // the SM count); sort_assign_chunk grows the buffer, keeping its contents, if needed
+  return c->bounds_part.reserve(sizeof(double) * 6 * (size_t) (row_keys_blocks((size_t) 1 << 40) + 64) * (nchunk + 1));
 }
 
 // def_box's checks for simulation boxes (src/genr_mesh.c:516-531), evaluated
@@ -697,12 +555,12 @@ template <typename F> double bisect_first(F pred) {
 // and 512 in double); the x pass, whose points lie a whole plane apart, is ours in
 // double up to 1536 and in single precision up to 1024 (where skipping the tiles
 // beyond the last bin edge outweighs cuFFT's faster float kernel), cuFFT's above.
-static bool fft_own_z(const psb_context *c, int ng, int precision) {
+bool fft_own_z(const psb_context *c, int ng, int precision) {
   if (c->opt_fft_own_z >= 0) return c->opt_fft_own_z != 0;
   return !(ng == 1024 || (ng == 512 && precision == 8));
 }
 
-static bool fft_own_x(const psb_context *c, int ng, int precision) {
+bool fft_own_x(const psb_context *c, int ng, int precision) {
   if (c->opt_fft_own_x >= 0) return c->opt_fft_own_x != 0;
   return precision == 8 ? ng <= 1536 : ng <= 1024;
 }
@@ -1094,7 +952,9 @@ int prepare_bins(psb_context *c, const psb_params *par) {
   return 0;
 }
 
-}  // namespace
+}  // namespace psb_host
+
+using namespace psb_host;
 
 // ---------------------------------------------------------------------------
 // C ABI
@@ -1670,7 +1530,9 @@ long psb_launch_count(const psb_context *c) { return c ? c->launches : -1; }
 // (powspec_b200/distributed.py); buffers are caller-owned device memory.
 // Simulation boxes only (BASELINE configs 4 and 5).
 // ---------------------------------------------------------------------------
-static int slab_geom(psb_context *c, const psb_params *par, const psb_slab *sl, AssignGeom &g) {
+}  // extern "C"
+namespace psb_host {
+int slab_geom(psb_context *c, const psb_params *par, const psb_slab *sl, AssignGeom &g) {
   if (check_params(par)) return -1;
   if (!par->issim) { set_error("the slab-decomposed path handles simulation boxes only\n"); return -1; }
   if (!sl || sl->nranks < 1 || sl->rank < 0 || sl->rank >= sl->nranks ||
@@ -1696,6 +1558,8 @@ static int slab_geom(psb_context *c, const psb_params *par, const psb_slab *sl, 
   }
   return 0;
 }
+}  // namespace psb_host
+extern "C" {
 
 size_t psb_slab_mesh_elems(const psb_params *par, const psb_slab *sl) {
   if (!par || !sl || sl->nranks < 1 || par->gsize % sl->nranks) return 0;
@@ -1758,7 +1622,9 @@ int psb_add(psb_context *c, void *dst, const void *src, size_t n, int precision)
   return 0;
 }
 
-static int slab_plans(psb_context *c, int ng, int nx, int prec) {
+}  // extern "C"
+namespace psb_host {
+int slab_plans(psb_context *c, int ng, int nx, int prec) {
   const bool own = c->opt_own_fft && fft_strided_supported(ng, prec);
   const bool own_x = own && fft_own_x(c, ng, prec), own_z = own && fft_own_z(c, ng, prec);
   if (c->slab_ng == ng && c->slab_nx == nx && c->slab_prec == prec && c->slab_own == own &&
@@ -1810,6 +1676,8 @@ static int slab_plans(psb_context *c, int ng, int nx, int prec) {
   c->slab_own_x = own_x; c->slab_own_z = own_z; c->slab_have = true;
   return 0;
 }
+}  // namespace psb_host
+extern "C" {
 
 // 2-D r2c over (y, z) of every owned x-plane, in place; `owned` points at the
 // first owned plane of the slab buffer

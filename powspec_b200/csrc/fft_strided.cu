@@ -256,7 +256,8 @@ template <int R3, int TK> struct Shape {
 template <typename T, int R3, int TK, int MINB>
 __global__ void __launch_bounds__(Shape<R3, TK>::THREADS, MINB)
 k_fft_strided(typename Mem<T>::gmem_t *__restrict__ data, int ngk, int outer_n, size_t outer_stride,
-    size_t estride, const double *__restrict__ k2a, const double *__restrict__ k2b, double k2max) {
+    size_t estride, const double *__restrict__ k2a, const double *__restrict__ k2b, double k2max,
+    FftOut out) {
   using S = Shape<R3, TK>;
   using E = El<T>;
   using MM = Mem<T>;
@@ -293,6 +294,11 @@ k_fft_strided(typename Mem<T>::gmem_t *__restrict__ data, int ngk, int outer_n, 
     la = (k0 + c) < ngk;
     lb = (k0 + c + TK) < ngk;
     return data + (size_t) o * outer_stride + k0 + c;
+  };
+  // offset of this thread's column inside a block of the transposed output layout
+  auto out_off = [&](long t) {
+    const int o = (int) (t / ktiles), k0 = (int) (t % ktiles) * WIDTH;
+    return (size_t) o * out.outer_stride + k0 + c;
   };
   E a[16];
   long tile = next_tile(blockIdx.x);
@@ -336,9 +342,22 @@ k_fft_strided(typename Mem<T>::gmem_t *__restrict__ data, int ngk, int outer_n, 
 #pragma unroll
       for (int tt = 0; tt < R3; tt++) d[tt] = sm_get(&col[p3 * ROW + tt + R3 * q1]);
       SmallDft<T, R3>::run(d);
+      if (out.ny == 0) {
 #pragma unroll
-      for (int q2 = 0; q2 < R3; q2++)
-        MM::store(g, (size_t) (p3 + 16 * q1 + 256 * q2) * estride, TK, la, lb, d[q2]);
+        for (int q2 = 0; q2 < R3; q2++)
+          MM::store(g, (size_t) (p3 + 16 * q1 + 256 * q2) * estride, TK, la, lb, d[q2]);
+      }
+      else {
+        // transposed output for the slab decomposition: point y of the transform goes to
+        // block y / ny (one per destination rank; the block may be peer memory), row y % ny
+        const size_t oo = out_off(tile);
+#pragma unroll
+        for (int q2 = 0; q2 < R3; q2++) {
+          const int y = p3 + 16 * q1 + 256 * q2, blk = y / out.ny;
+          MM::store(static_cast<G *>(out.base[blk]) + oo, (size_t) (y - blk * out.ny) * ngk, TK, la, lb,
+              d[q2]);
+        }
+      }
     }
     __syncthreads();
     tile = ntl; g = ng_; la = nla; lb = nlb;
@@ -347,7 +366,7 @@ k_fft_strided(typename Mem<T>::gmem_t *__restrict__ data, int ngk, int outer_n, 
 
 template <typename T, int R3, int TK, int MINB>
 int launch_shape(void *data, int ng, int ngk, int axis, int outer_n, const double *k2a,
-    const double *k2b, double k2max, cudaStream_t st) {
+    const double *k2b, double k2max, const FftOut &out, cudaStream_t st) {
   using S = Shape<R3, TK>;
   using G = typename Mem<T>::gmem_t;
   const size_t smem = (size_t) TK * S::PITCH * 16;
@@ -367,10 +386,10 @@ int launch_shape(void *data, int ng, int ngk, int axis, int outer_n, const doubl
   //         outer index = the row inside the plane.
   if (axis == 1)
     kern<<<grid, S::THREADS, smem, st>>>(static_cast<G *>(data), ngk, outer_n,
-        (size_t) ng * ngk, row, nullptr, nullptr, 0.0);
+        (size_t) ng * ngk, row, nullptr, nullptr, 0.0, out);
   else
     kern<<<grid, S::THREADS, smem, st>>>(static_cast<G *>(data), ngk, outer_n, row,
-        (size_t) outer_n * ngk, k2a, k2b, k2max);
+        (size_t) outer_n * ngk, k2a, k2b, k2max, FftOut{});
   PSB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -802,14 +821,14 @@ int launch_rows_any(const void *src, void *dst, int ng, long nrows, size_t src_p
 
 template <typename T>
 int launch_any(void *data, int ng, int ngk, int axis, int outer_n, const double *k2a,
-    const double *k2b, double k2max, cudaStream_t st) {
+    const double *k2b, double k2max, const FftOut &out, cudaStream_t st) {
   switch (ng) {
-    case 512: return launch_shape<T, 2, 16, 1>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, st);
+    case 512: return launch_shape<T, 2, 16, 1>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, out, st);
     case 1024:
-      if (g_fft_variant == 1) return launch_shape<T, 4, 4, 2>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, st);
-      return launch_shape<T, 4, 8, 1>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, st);
-    case 1536: return launch_shape<T, 6, 4, 1>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, st);
-    case 2048: return launch_shape<T, 8, 4, 1>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, st);
+      if (g_fft_variant == 1) return launch_shape<T, 4, 4, 2>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, out, st);
+      return launch_shape<T, 4, 8, 1>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, out, st);
+    case 1536: return launch_shape<T, 6, 4, 1>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, out, st);
+    case 2048: return launch_shape<T, 8, 4, 1>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, out, st);
     default:
       set_error("no hand-written strided FFT for GRID_SIZE %d\n", ng);
       return -1;
@@ -831,8 +850,24 @@ bool fft_strided_supported(int ng, int precision) {
 int launch_fft_strided(void *data, int precision, int ng, int ngk, int axis, int outer_n,
     const double *k2a, const double *k2b, double k2max, cudaStream_t st) {
   if (precision == 8)
-    return launch_any<double>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, st);
-  return launch_any<float>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, st);
+    return launch_any<double>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, FftOut{}, st);
+  return launch_any<float>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, FftOut{}, st);
+}
+
+// The y pass of the slab-decomposed transform with the transpose's packing (and, when
+// the blocks are peer memory, the transpose itself) fused into its store: reads
+// (outer_n, ng, ngk) from `data`, writes point y of plane o to
+// out.base[y / out.ny] + (o * out.outer_stride + (y % out.ny) * ngk + k).
+int launch_fft_strided_out(const void *data, int precision, int ng, int ngk, int outer_n,
+    const FftOut &out, cudaStream_t st) {
+  if (out.ny <= 0 || ng % out.ny || ng / out.ny > FftOut::MAXB) {
+    set_error("invalid transposed-output layout for the y pass\n");
+    return -1;
+  }
+  void *d = const_cast<void *>(data);
+  if (precision == 8)
+    return launch_any<double>(d, ng, ngk, 1, outer_n, nullptr, nullptr, 0.0, out, st);
+  return launch_any<float>(d, ng, ngk, 1, outer_n, nullptr, nullptr, 0.0, out, st);
 }
 
 // z and y passes of nplanes planes of a (nplanes, ng, 2 ngk) real mesh in place,

@@ -14,6 +14,7 @@ namespace psb {
 // ---------------------------------------------------------------------------
 void set_error(const char *fmt, ...);
 const char *get_error();
+void errors_quiet(bool on);      // record messages without printing them (this thread)
 
 #define PSB_CUDA(call)                                                          \
   do {                                                                          \
@@ -126,6 +127,15 @@ double ylm_norm(int l, int m);
 // or x (axis 0, array (ng, outer_n, ngk)) of a complex array; optional tile skipping
 // for the x pass (k2a[outer] + k2b[k] >= k2max)
 bool fft_strided_supported(int ng, int precision);
+// transposed output of the y pass (slab decomposition): ng / ny blocks of (outer, ny, ngk)
+struct FftOut {
+  static constexpr int MAXB = 16;
+  void *base[MAXB] = {};        // block q = rows [q ny, (q+1) ny) of the transformed axis
+  int ny = 0;                   // 0: in place
+  size_t outer_stride = 0;      // elements between outer indices inside a block (ny * ngk)
+};
+int launch_fft_strided_out(const void *data, int precision, int ng, int ngk, int outer_n,
+    const FftOut &out, cudaStream_t st);
 void fft_set_variant(int v);
 int launch_fft_strided(void *data, int precision, int ng, int ngk, int axis, int outer_n,
     const double *k2a, const double *k2b, double k2max, cudaStream_t st);

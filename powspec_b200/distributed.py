@@ -310,7 +310,7 @@ class GpuSlabEngine:
 
     def finish(self, pl, xpl, wdata):
         """pl: list of per-catalogue allreduced tensors (or None), xpl likewise."""
-        from .api import PK, GET_K, GET_KEDGE, GET_KM, GET_CNT, GET_LCNT, GET_PL, GET_XPL, GET_SHOT, GET_NORM, _err
+        from .api import _err, pk_from_result
         host = [None if p is None else np.ascontiguousarray(p.cpu().numpy()) for p in pl] + \
                [None if xpl is None else np.ascontiguousarray(xpl.cpu().numpy())]
         while len(host) < 3:
@@ -321,23 +321,7 @@ class GpuSlabEngine:
         if not r:
             raise _err(self.L, "psb_slab_finish")
         try:
-            L = self.L
-            nbin, nl = L.psb_result_nbin(r), L.psb_result_nl(r)
-
-            def get(what, n, dtype=np.float64, idx=0):
-                a = np.empty(n, dtype=dtype)
-                return a if L.psb_result_get(r, what, idx, a.ctypes.data) >= 0 else None
-
-            pls = []
-            for i in range(2):
-                q = get(GET_PL, nl * nbin, idx=i)
-                pls.append(None if q is None else q.reshape(nl, nbin))
-            x = get(GET_XPL, nl * nbin)
-            return PK(nl=nl, nbin=nbin, poles=list(self.conf.poles), k=get(GET_K, nbin),
-                      kedge=get(GET_KEDGE, nbin + 1), km=get(GET_KM, nbin),
-                      cnt=get(GET_CNT, nbin, np.uint64), lcnt=get(GET_LCNT, nl * nbin).reshape(nl, nbin),
-                      pl=pls, xpl=None if x is None else x.reshape(nl, nbin),
-                      shot=get(GET_SHOT, 2), norm=get(GET_NORM, 2))
+            return pk_from_result(self.L, r, self.conf)
         finally:
             self.L.psb_result_free(r)
 

@@ -70,3 +70,61 @@ def test_nccl_slabs_match_oracle(port_oracle):
     r.__dict__.update(got)
     want = port_oracle.run(_catalogue(), **KW)
     assert_spectra_close(r, want, TOL_DOUBLE, f"nccl slabs x{world}")
+
+
+def _worker_lib(rank, world, port, q, p2p):
+    """The in-library path: the library issues the NCCL calls itself (csrc/dist.cu)."""
+    import torch
+    import torch.distributed as dist
+
+    import powspec_b200 as pb
+    from powspec_b200.dist import NcclRank
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        d = _catalogue()
+        share = np.array_split(d, world)[rank]
+        ctx = pb.Context(rank)
+        conf = pb.Conf(ndata=1, issim=True, bsize=(BOX,) * 3, gsize=NG, assign=2, intlace=True,
+                       poles=(0, 2, 4), kbin=0.02, device=rank)
+        eng = NcclRank.from_torch(ctx)
+        eng.set_option("p2p", p2p)
+        halves = np.array_split(share, 2)           # two chunks per rank
+        pk = eng.run(conf, [[torch.from_numpy(h).cuda() for h in halves]], [float(d[:, 3].sum())])
+        if rank == 0:
+            q.put(dict(nbin=pk.nbin, nl=pk.nl, k=pk.k, kedge=pk.kedge, km=pk.km, cnt=pk.cnt,
+                       lcnt=pk.lcnt, pl=pk.pl, xpl=pk.xpl, shot=pk.shot, norm=pk.norm,
+                       traffic=pk.traffic))
+        eng.close()
+        ctx.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("p2p", [0, 1])
+def test_library_nccl_slabs_match_oracle(port_oracle, p2p):
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mpc = mp.get_context("spawn")
+    q = mpc.Queue()
+    procs = [mpc.Process(target=_worker_lib, args=(r, world, port, q, p2p)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=300)
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+
+    class R:
+        pass
+    r = R()
+    r.__dict__.update(got)
+    want = port_oracle.run(_catalogue(), **KW)
+    assert_spectra_close(r, want, TOL_DOUBLE, f"library nccl slabs x{world} p2p={p2p}")

@@ -7,6 +7,8 @@
 //           an instruction hit 32 unrelated cells (bank conflicts, rare CAS clashes)
 //   mode 1: one particle per warp, one stencil point per lane (27 of 32 lanes active,
 //           distinct cells: 3 contiguous in z x 3 rows x 3 planes)
+//   mode 2 / 3: the same two patterns with plain (non-atomic) load-add-store; T = unsigned
+//           uses the native ATOMS.ADD (fp64, fp32 and u64 adds are ATOMS.CAST.SPIN loops)
 // Prints elements/s over the whole GPU and the time 5.4e9 updates (config 2) would take.
 //   nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o tools/smem_atomic_probe tools/smem_atomic_probe.cu
 #include <cuda_runtime.h>
@@ -42,6 +44,38 @@ __global__ void __launch_bounds__(256, 2) k_tile(double *out, int ppb, unsigned 
             atomicAdd(&sm[((bx + a) * EY + (by + b)) * EZ + bz + c], w);
     }
   }
+  else if (MODE == 2) {
+    // plain read-modify-write, one particle per lane: NOT race-free (lanes and warps may
+    // collide) — the rate a conflict-free colouring of the same accesses could reach
+    for (int p = threadIdx.x; p < ppb; p += blockDim.x) {
+      const unsigned h = mix(seed + blockIdx.x * 1000003u + (unsigned) p);
+      const int bx = 1 + (int) (h % 16u), by = 1 + (int) ((h >> 8) % 16u), bz = 1 + (int) ((h >> 16) % 32u);
+      const T w = (T) (1.0 + (double) (h & 7u));
+#pragma unroll
+      for (int a = -1; a <= 1; a++)
+#pragma unroll
+        for (int b = -1; b <= 1; b++)
+#pragma unroll
+          for (int c = -1; c <= 1; c++) {
+            volatile T *q = &sm[((bx + a) * EY + (by + b)) * EZ + bz + c];
+            *q = *q + w;
+          }
+    }
+  }
+  else if (MODE == 3) {
+    // plain read-modify-write, one particle per warp and lane = stencil point (distinct
+    // cells inside an instruction; warps of a block may still collide: rate probe only)
+    const int a = lane / 9 - 1, b = (lane / 3) % 3 - 1, c = lane % 3 - 1;
+    for (int p = warp; p < ppb; p += nw) {
+      const unsigned h = mix(seed + blockIdx.x * 1000003u + (unsigned) p);
+      const int bx = 1 + (int) (h % 16u), by = 1 + (int) ((h >> 8) % 16u), bz = 1 + (int) ((h >> 16) % 32u);
+      const T w = (T) (1.0 + (double) (h & 7u));
+      if (lane < 27) {
+        volatile T *q = &sm[((bx + a) * EY + (by + b)) * EZ + bz + c];
+        *q = *q + w;
+      }
+    }
+  }
   else {
     const int a = lane / 9 - 1, b = (lane / 3) % 3 - 1, c = lane % 3 - 1;
     for (int p = warp; p < ppb; p += nw) {
@@ -52,9 +86,20 @@ __global__ void __launch_bounds__(256, 2) k_tile(double *out, int ppb, unsigned 
     }
   }
   __syncthreads();
+  // checksum: ONE global atomic per block (one per thread — 1.2 million adds to a single
+  // address — serialised at the L2 for ~1.9 ms and was what the first version of this
+  // probe measured, whatever the shared-memory pattern)
   double s = 0.0;
   for (int i = threadIdx.x; i < E; i += blockDim.x) s += (double) sm[i];
-  atomicAdd(out, s);
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  __shared__ double part[8];
+  if (lane == 0) part[warp] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w2 = 0; w2 < nw; w2++) t += part[w2];
+    atomicAdd(out, t);
+  }
 }
 
 template <typename T, int MODE> void run(const char *what, int sms) {
@@ -99,5 +144,10 @@ int main() {
   run<double, 1>("f64, one particle per warp (lane = stencil pt)", sms);
   run<float, 0>("f32, one particle per lane", sms);
   run<float, 1>("f32, one particle per warp", sms);
+  run<unsigned, 0>("u32 native ATOMS.ADD, one particle per lane", sms);
+  run<unsigned, 1>("u32 native ATOMS.ADD, one particle per warp", sms);
+  run<double, 2>("f64 PLAIN rmw (racy), one particle per lane", sms);
+  run<double, 3>("f64 PLAIN rmw, lane = stencil point", sms);
+  run<float, 2>("f32 PLAIN rmw (racy), one particle per lane", sms);
   return 0;
 }
