@@ -165,6 +165,8 @@ enum {
 int psb_timings(const psb_context *ctx, double *ms, int n);
 /* number of kernel launches (ours + cuFFT calls counted as 1) of the last run */
 long psb_launch_count(const psb_context *ctx);
+/* the context's compute stream (a cudaStream_t), e.g. to record timing events on it */
+void *psb_stream(const psb_context *ctx);
 
 /* Tunables (tests / ablations; the list is in psb_set_option, csrc/context.cu):
  * "sort", "strip", "coop", "own_fft", "fft_fused", "stream", "stream_chunk",
@@ -231,6 +233,9 @@ int psb_dist_set_option(psb_dist *d, const char *name, long value);
 int psb_dist_begin(psb_dist *d, const psb_params *par);
 /* one chunk of THIS rank's share of catalogue `cat`: device memory, any distribution */
 int psb_dist_add(psb_dist *d, int cat, const double *particles_dev, size_t n);
+/* the same from host memory, in nchunks pieces (same number on every rank) whose uploads
+ * overlap the routing and scatter of the previous piece */
+int psb_dist_add_host(psb_dist *d, int cat, const double *particles_host, size_t n, int nchunks);
 /* wdata: global sum of weights per catalogue; every rank gets the same result */
 psb_result *psb_dist_finish(psb_dist *d, const double wdata[2]);
 /* CUDA-event stage times of the last run on this rank, ms */

@@ -128,6 +128,8 @@ def load_library():
     L.psb_launch_count.restype = C.c_long
     L.psb_launch_count.argtypes = [C.c_void_p]
     L.psb_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_long]
+    L.psb_stream.restype = C.c_void_p
+    L.psb_stream.argtypes = [C.c_void_p]
     L.psb_generate_catalog.restype = C.c_void_p
     L.psb_generate_catalog.argtypes = [C.c_void_p, C.c_size_t, C.c_double, C.c_int, C.c_uint64]
     L.psb_device_free.argtypes = [C.c_void_p, C.c_void_p]
@@ -148,6 +150,7 @@ def load_library():
     L.psb_dist_set_option.argtypes = [vp, C.c_char_p, C.c_long]
     L.psb_dist_begin.argtypes = [vp, C.POINTER(_Params)]
     L.psb_dist_add.argtypes = [vp, C.c_int, vp, C.c_size_t]
+    L.psb_dist_add_host.argtypes = [vp, C.c_int, vp, C.c_size_t, C.c_int]
     L.psb_dist_finish.restype = vp
     L.psb_dist_finish.argtypes = [vp, C.POINTER(C.c_double)]
     L.psb_dist_timings.argtypes = [vp, vp, C.c_int]
@@ -372,6 +375,11 @@ class Context:
     def set_option(self, name: str, value: int):
         if self.L.psb_set_option(self.h, name.encode(), int(value)):
             raise _err(self.L, "psb_set_option")
+
+    def torch_stream(self):
+        """The library's compute stream as a torch stream (timing events, ordering)."""
+        import torch
+        return torch.cuda.ExternalStream(self.L.psb_stream(self.h), device=torch.device("cuda", self.device))
 
     # -- genr_mesh
     def genr_mesh(self, conf: Conf, cata: Cata) -> Mesh:

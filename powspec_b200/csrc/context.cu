@@ -1522,6 +1522,10 @@ int psb_timings(const psb_context *c, double *ms, int n) {
 
 long psb_launch_count(const psb_context *c) { return c ? c->launches : -1; }
 
+// the compute stream as a cudaStream_t (for hosts that want to record their own events on
+// it or order their own work after the library's)
+void *psb_stream(const psb_context *c) { return c ? (void *) c->st : nullptr; }
+
 
 // ---------------------------------------------------------------------------
 // Slab-decomposed mesh: building blocks for one rank.  The

@@ -635,6 +635,45 @@ int psb_dist_add(psb_dist *d, int cat, const double *particles, size_t n) {
   return 0;
 }
 
+// The same from HOST memory (pinned or pageable): this rank's share is cut into
+// `nchunks` pieces (the same number on every rank — the call is collective), uploaded
+// on the copy stream into two alternating device buffers while the previous piece is
+// being routed and scattered.
+int psb_dist_add_host(psb_dist *d, int cat, const double *particles_host, size_t n, int nchunks) {
+  if (!d || !d->begun) { set_error("psb_dist_begin has not been called\n"); return -1; }
+  psb_context *c = d->c;
+  PSB_CUDA(cudaSetDevice(c->device));
+  if (nchunks < 1) nchunks = 1;
+  const size_t per = (n + nchunks - 1) / nchunks;
+  const bool pinned = n && is_pinned(particles_host);
+  for (int s = 0; s < 2; s++) {
+    if (c->chunkbuf[s].reserve((per ? per : 1) * 32)) return dist_fail(d);
+    if (!c->ev_filled[s]) {
+      PSB_CUDA(cudaEventCreateWithFlags(&c->ev_filled[s], cudaEventDisableTiming));
+      PSB_CUDA(cudaEventCreateWithFlags(&c->ev_consumed[s], cudaEventDisableTiming));
+    }
+  }
+  for (int k = 0; k < nchunks; k++) {
+    const size_t lo = std::min(n, per * k), hi = std::min(n, lo + per), len = hi - lo;
+    const int s = k & 1;
+    double *buf = c->chunkbuf[s].as<double>();
+    if (len) {
+      PSB_CUDA(cudaStreamWaitEvent(c->st_copy, c->ev_consumed[s], 0));
+      {
+        StageScope scope(c, PSB_T_H2D, c->st_copy);
+        if (h2d_async(c, buf, particles_host + 4 * lo, len * 32, pinned, c->st_copy)) return dist_fail(d);
+      }
+      PSB_CUDA(cudaEventRecord(c->ev_filled[s], c->st_copy));
+      PSB_CUDA(cudaStreamWaitEvent(c->st, c->ev_filled[s], 0));
+    }
+    if (psb_dist_add(d, cat, buf, len)) return -1;
+    // the chunk is read by the partition kernels only, which psb_dist_add has waited for
+    // (G > 1) or which precede this record on the stream (G == 1)
+    if (len) PSB_CUDA(cudaEventRecord(c->ev_consumed[s], c->st));
+  }
+  return 0;
+}
+
 }  // extern "C"
 
 namespace {
@@ -1029,20 +1068,17 @@ int psb_group_mesh(psb_group *g, const psb_params *par, const psb_cats *cats) {
       const size_t per = (N + g->n - 1) / g->n;
       const size_t a = std::min(N, per * r), b = std::min(N, per * (r + 1));
       const size_t nchunk = std::max<size_t>(1, (per + CH - 1) / CH);     // the same on every rank
-      const bool pinned = cats->memspace == PSB_MEM_HOST && is_pinned(cats->data[i]);
+      if (cats->memspace == PSB_MEM_HOST) {
+        if (psb_dist_add_host(d, i, cats->data[i] + 4 * a, b - a, (int) nchunk)) return -1;
+        continue;
+      }
+      // device memory of one GPU: every rank pulls its share chunk by chunk
       for (size_t k = 0; k < nchunk; k++) {
         const size_t lo = std::min(b, a + k * CH), hi = std::min(b, lo + CH), len = hi - lo;
         DevBuf &buf = g->chunk[k & 1][r];
         if (buf.reserve(std::min(per, CH) * 32 + 32)) return -1;
-        if (len) {
-          // the chunk buffer's previous reader (two chunks back) has finished: psb_dist_add
-          // waits on the stream once per chunk
-          if (cats->memspace == PSB_MEM_HOST) {
-            StageScope scope(c, PSB_T_H2D, c->st);
-            if (h2d_async(c, buf.p, cats->data[i] + 4 * lo, len * 32, pinned, c->st)) return -1;
-          }
-          else PSB_CUDA(cudaMemcpyAsync(buf.p, cats->data[i] + 4 * lo, len * 32, cudaMemcpyDefault, c->st));
-        }
+        // stream order protects the buffer: its previous readers precede this copy on c->st
+        if (len) PSB_CUDA(cudaMemcpyAsync(buf.p, cats->data[i] + 4 * lo, len * 32, cudaMemcpyDefault, c->st));
         if (psb_dist_add(d, i, buf.as<double>(), len)) return -1;
       }
     }

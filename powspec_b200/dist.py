@@ -161,6 +161,14 @@ class NcclRank:
         if self.L.psb_dist_add(self.h, cat, ptr, n):
             raise _err(self.L, "psb_dist_add", POWSPEC_ERR_MESH)
 
+    def add_host(self, cat: int, particles, nchunks: int = 1):
+        """particles: (n, 4) float64 host array / CPU tensor (pinned or pageable)."""
+        ptr, n, sp, keep = _ptr_of(particles)
+        if n and sp != 0:
+            raise PowspecB200Error("psb_dist_add_host takes host-resident particles")
+        if self.L.psb_dist_add_host(self.h, cat, ptr, n, int(nchunks)):
+            raise _err(self.L, "psb_dist_add_host", POWSPEC_ERR_MESH)
+
     def finish(self, wdata):
         w = (C.c_double * 2)(*(list(wdata) + [0.0])[:2])
         r = self.L.psb_dist_finish(self.h, w)
