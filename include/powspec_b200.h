@@ -167,9 +167,11 @@ int psb_timings(const psb_context *ctx, double *ms, int n);
 long psb_launch_count(const psb_context *ctx);
 /* the context's compute stream (a cudaStream_t), e.g. to record timing events on it */
 void *psb_stream(const psb_context *ctx);
+/* the scatter the last psb_mesh used: 0 = global reductions, 1 = owner-computes tiles */
+int psb_assign_path(const psb_context *ctx);
 
 /* Tunables (tests / ablations; the list is in psb_set_option, csrc/context.cu):
- * "sort", "strip", "coop", "own_fft", "fft_fused", "stream", "stream_chunk",
+ * "sort", "strip", "coop", "owner", "own_fft", "fft_fused", "stream", "stream_chunk",
  * "stream_taper", "h2d_threads", "survey_direct", "geom_sym" ...; returns non-zero
  * for an unknown name */
 int psb_set_option(psb_context *ctx, const char *name, long value);

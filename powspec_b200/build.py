@@ -21,7 +21,7 @@ ROOT = os.path.dirname(HERE)
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libpowspec_b200.so")
 
-SOURCES = ["assign.cu", "binning.cu", "fft_strided.cu", "cnvt.cu", "ingest.cu", "generate.cu", "context.cu", "dist.cu", "refabi.cpp"]
+SOURCES = ["assign.cu", "assign_tiles.cu", "binning.cu", "fft_strided.cu", "cnvt.cu", "ingest.cu", "generate.cu", "context.cu", "dist.cu", "refabi.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -51,7 +51,7 @@ def _stale(target: str, deps) -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = _nvcc()
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, "psb_internal.h"), os.path.join(CSRC, "psb_context.h"),
+    headers = [os.path.join(CSRC, "psb_internal.h"), os.path.join(CSRC, "psb_context.h"), os.path.join(CSRC, "assign_common.cuh"),
                os.path.join(ROOT, "include", "powspec_b200.h"),
                os.path.join(ROOT, "include", "powspec_refabi.h")]
     # the image exports CC/CXX pointing at a wrapper; pin the system compiler

@@ -19,7 +19,7 @@
 // round-to-nearest intrinsics in the reference's operation order
 // ((x - origin) * Ng / L), so no FMA contraction can move a particle.
 
-#include "psb_internal.h"
+#include "assign_common.cuh"
 
 #include <cfloat>
 
@@ -71,24 +71,6 @@ int launch_bounds(const double *p, size_t n, double *partials, int nblk,
   k_bounds<<<nblk, 256, 0, st>>>(reinterpret_cast<const double2 *>(p), n, partials);
   PSB_CUDA(cudaGetLastError());
   return 0;
-}
-
-// ---------------------------------------------------------------------------
-// grid coordinate and base cell, in the reference's operation order
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ double grid_coord(double x, double org, double len, int ng) {
-  // (x - org) * Ng / L : src/genr_mesh.c:57,91,152,256
-  return __ddiv_rn(__dmul_rn(__dsub_rn(x, org), (double) ng), len);
-}
-
-__device__ __forceinline__ int base_cell(double t, int ng) {
-  int c = (int) t;
-  // quirk Q8: a coordinate that rounds to t == Ng indexes out
-  // of bounds in the reference; wrap it instead
-  if (c >= ng) c -= ng;
-  // coordinates outside the box are rejected by def_box's checks (evaluated
-  // after the scatter for simulation boxes): never index out of bounds meanwhile
-  return min(max(c, 0), ng - 1);
 }
 
 // ---------------------------------------------------------------------------
@@ -154,10 +136,10 @@ __global__ void __launch_bounds__(256) k_row_scatter(const double2 *__restrict__
     double2 *__restrict__ out) {
   for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n;
        i += (size_t) gridDim.x * blockDim.x) {
-    double2 a = __ldg(p + 2 * i), b = __ldg(p + 2 * i + 1);
+    double2 a, b;
+    ld_record(p, i, a, b);
     uint32_t pos = atomicAdd(cursor + keys[i], 1u);
-    out[2 * (size_t) pos] = a;
-    out[2 * (size_t) pos + 1] = b;
+    st_record(out, pos, a, b);
   }
 }
 
@@ -184,55 +166,6 @@ int launch_row_scatter(const double *p, size_t n, const uint32_t *keys,
       reinterpret_cast<double2 *>(sorted));
   PSB_CUDA(cudaGetLastError());
   return 0;
-}
-
-// ---------------------------------------------------------------------------
-// one axis of the assignment stencil: cells (periodic) and weights
-// ---------------------------------------------------------------------------
-template <int SCHEME> struct Stencil { static constexpr int N = SCHEME + 1; };
-
-__device__ __forceinline__ int wrap_up(int c, int ng) { return (c == ng - 1) ? 0 : c + 1; }
-__device__ __forceinline__ int wrap_dn(int c, int ng) { return (c == 0) ? ng - 1 : c - 1; }
-
-template <int SCHEME>
-__device__ __forceinline__ void axis_stencil(double t, int ng, int (&idx)[SCHEME + 1],
-    double (&w)[SCHEME + 1]) {
-  int c = (int) t;
-  double d = t - (double) c;    // exact
-  if (c >= ng) c -= ng;         // Q8 guard, see base_cell()
-  c = min(max(c, 0), ng - 1);
-  if constexpr (SCHEME == 0) {  // NGP, src/genr_mesh.c:60-66
-    if (d >= 0.5) c = wrap_up(c, ng);
-    idx[0] = c; w[0] = 1.0;
-  }
-  else if constexpr (SCHEME == 1) {     // CIC, src/genr_mesh.c:98-108
-    idx[0] = c; idx[1] = wrap_up(c, ng);
-    w[1] = d; w[0] = 1.0 - d;
-  }
-  else if constexpr (SCHEME == 2) {     // TSC, src/genr_mesh.c:157-173
-    double h;
-    if (d < 0.5) {
-      idx[1] = c; idx[0] = wrap_dn(c, ng); idx[2] = wrap_up(c, ng);
-      h = 0.5 - d;
-    }
-    else {
-      idx[0] = c; idx[1] = wrap_up(c, ng); idx[2] = wrap_up(idx[1], ng);
-      d = 1.0 - d;
-      h = 0.5 + d;
-    }
-    w[0] = h * (h * 0.5);
-    w[1] = 0.75 - d * d;
-    w[2] = 1.0 - w[0] - w[1];
-  }
-  else {                                // PCS, src/genr_mesh.c:256-272 (units of 1/6)
-    idx[1] = c; idx[0] = wrap_dn(c, ng); idx[2] = wrap_up(c, ng);
-    idx[3] = wrap_up(idx[2], ng);
-    double d2 = d * d;
-    w[3] = d2 * d;
-    w[2] = 1.0 + 3.0 * (d + d2 - w[3]);
-    w[1] = 4.0 - 6.0 * d2 + 3.0 * w[3];
-    w[0] = 6.0 - w[1] - w[2] - w[3];
-  }
 }
 
 // x-plane of the global mesh -> plane of the local buffer (slab decomposition:
@@ -315,71 +248,6 @@ __global__ void __launch_bounds__(256) k_assign(const double2 *__restrict__ p, s
 // 1e-9 of a value that decides a cell (0, 1/2, 1), so the cell a particle lands
 // in is always the reference's.
 // ---------------------------------------------------------------------------
-struct AxisXform { double org, ng, len, inv_len; };
-
-__device__ __forceinline__ void split_floor(double t, int &c, double &d) {
-  const double MAGIC = 6755399441055744.0;      // 1.5 * 2^52: integer part lands in the low word
-  const double tm = __dadd_rn(t, MAGIC);
-  c = __double2loint(tm);
-  double r = __dsub_rn(tm, MAGIC);
-  if (r > t) { r -= 1.0; c -= 1; }
-  d = t - r;                                    // exact
-}
-
-__device__ __forceinline__ void grid_split(double x, const AxisXform &ax, int &c, double &d) {
-  const double a = __dmul_rn(__dsub_rn(x, ax.org), ax.ng);
-  // a / len, correctly rounded in all but pathological cases (Markstein)
-  const double q0 = a * ax.inv_len;
-  const double e = __fma_rn(-q0, ax.len, a);
-  double t = __fma_rn(e, ax.inv_len, q0);
-  split_floor(t, c, d);
-  if (d < 1e-9 || d > 1.0 - 1e-9 || fabs(d - 0.5) < 1e-9) {
-    t = __ddiv_rn(a, ax.len);                   // the reference's own arithmetic
-    c = (int) t;
-    d = t - (double) c;
-  }
-}
-
-// stencil from (base cell, fraction); same formulas as axis_stencil()
-template <int SCHEME>
-__device__ __forceinline__ void stencil_from(int c, double d, int ng, int (&idx)[SCHEME + 1],
-    double (&w)[SCHEME + 1]) {
-  if (c >= ng) c -= ng;         // quirk Q8 guard
-  c = min(max(c, 0), ng - 1);   // out-of-box input: stay in bounds, def_box rejects it later
-  if constexpr (SCHEME == 0) {
-    if (d >= 0.5) c = wrap_up(c, ng);
-    idx[0] = c; w[0] = 1.0;
-  }
-  else if constexpr (SCHEME == 1) {
-    idx[0] = c; idx[1] = wrap_up(c, ng);
-    w[1] = d; w[0] = 1.0 - d;
-  }
-  else if constexpr (SCHEME == 2) {
-    double h;
-    if (d < 0.5) {
-      idx[1] = c; idx[0] = wrap_dn(c, ng); idx[2] = wrap_up(c, ng);
-      h = 0.5 - d;
-    }
-    else {
-      idx[0] = c; idx[1] = wrap_up(c, ng); idx[2] = wrap_up(idx[1], ng);
-      d = 1.0 - d;
-      h = 0.5 + d;
-    }
-    w[0] = h * (h * 0.5);
-    w[1] = 0.75 - d * d;
-    w[2] = 1.0 - w[0] - w[1];
-  }
-  else {
-    idx[1] = c; idx[0] = wrap_dn(c, ng); idx[2] = wrap_up(c, ng);
-    idx[3] = wrap_up(idx[2], ng);
-    double d2 = d * d;
-    w[3] = d2 * d;
-    w[2] = 1.0 + 3.0 * (d + d2 - w[3]);
-    w[1] = 4.0 - 6.0 * d2 + 3.0 * w[3];
-    w[0] = 6.0 - w[1] - w[2] - w[3];
-  }
-}
-
 template <int SCHEME, typename real>
 __device__ __forceinline__ void scatter_coop(const double x[3], double pw, const double org[3],
     const AssignGeom &g, int zsel, real *__restrict__ mesh) {
@@ -433,7 +301,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) k_assign_coop(const double2 *__re
 #pragma unroll
   for (int it = 0; it < ITER; it++) {
     const size_t i = first + (size_t) it * PPW;
-    if (sub < PPW && i < n) { a[it] = __ldg(p + 2 * i); b[it] = __ldg(p + 2 * i + 1); }
+    if (sub < PPW && i < n) ld_record(p, i, a[it], b[it]);
   }
 #pragma unroll
   for (int it = 0; it < ITER; it++) {
@@ -573,8 +441,9 @@ __global__ void __launch_bounds__(256) k_owner_scatter(const double2 *__restrict
     const size_t i = tile + (size_t) q * 256 + threadIdx.x;
     if (i < n) {
       const size_t pos = (size_t) base[key[q]] + slot[q];
-      out[2 * pos] = __ldg(p + 2 * i);
-      out[2 * pos + 1] = __ldg(p + 2 * i + 1);
+      double2 a, b;
+      ld_record(p, i, a, b);
+      st_record(out, pos, a, b);
     }
   }
 }

@@ -279,10 +279,86 @@ int convert_arrays(psb_context *c, const psb_cosmo *cm, double *const *arr, cons
 // `consumed` (optional) is recorded once the source buffer is no longer read.
 // `bounds` (optional): the chunk's coordinate bounds are appended to
 // c->bounds_part (6 doubles per block); bounds_finish() reduces them.
+int zero_if_fresh(psb_context *c, const AssignGeom &g, int precision, void *m0, void *m1, bool *fresh) {
+  if (!fresh || !*fresh) return 0;
+  const size_t bytes = (size_t) g.nxloc * g.ng * g.rowlen * precision;
+  for (void *m : {m0, m1}) {
+    if (!m) continue;
+    StageScope sc(c, PSB_T_MEMSET, c->st);
+    PSB_CUDA(cudaMemsetAsync(m, 0, bytes, c->st));
+  }
+  *fresh = false;
+  return 0;
+}
+
+// Owner-computes path (assign_tiles.cu): tile lists (count, scan, fill), then one block
+// per (tile, field) accumulates in shared memory and writes the tile once.
+int tile_assign_chunk(psb_context *c, const double *src, size_t len, const AssignGeom &g,
+    int scheme, int precision, double wscale, void *m0, void *m1, cudaEvent_t consumed,
+    double *partials, bool *fresh) {
+  const size_t ntile = tile_list_count(g);
+  const int nblk = row_keys_blocks(len);
+  if (c->tile_cnt.reserve((ntile + 1) * 4) || c->tile_start.reserve((ntile + 1) * 4) ||
+      c->wmax_buf.reserve(sizeof(double) * (nblk + 1)))
+    return -1;
+  size_t tmp_bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, c->tile_cnt.as<uint32_t>(), c->tile_start.as<uint32_t>(),
+      (int) ntile + 1, c->st);
+  if (c->cubtmp.reserve(tmp_bytes)) return -1;
+  double *wmax = c->wmax_buf.as<double>();
+  uint32_t total = 0;
+  {
+    StageScope sc(c, PSB_T_SORT, c->st);
+    PSB_CUDA(cudaMemsetAsync(c->tile_cnt.p, 0, (ntile + 1) * 4, c->st));
+    if (launch_tile_count(src, len, g, scheme, m1 != nullptr, c->tile_cnt.as<uint32_t>(), partials, wmax + 1,
+          wmax, c->st))
+      return -1;
+    PSB_CUDA(cub::DeviceScan::ExclusiveSum(c->cubtmp.p, tmp_bytes, c->tile_cnt.as<uint32_t>(),
+        c->tile_start.as<uint32_t>(), (int) ntile + 1, c->st));
+    // the list buffer is sized from the total: one small host wait per chunk
+    PSB_CUDA(cudaMemcpyAsync(&total, c->tile_start.as<uint32_t>() + ntile, 4, cudaMemcpyDeviceToHost, c->st));
+    PSB_CUDA(cudaStreamSynchronize(c->st));
+    if (c->sorted.reserve((size_t) (total ? total : 1) * 32)) return -1;
+  }
+  {
+    StageScope sc(c, PSB_T_SORT, c->st);
+    PSB_CUDA(cudaMemcpyAsync(c->tile_cnt.p, c->tile_start.p, (ntile + 1) * 4, cudaMemcpyDeviceToDevice, c->st));
+    if (launch_tile_fill(src, len, g, scheme, m1 != nullptr, c->tile_cnt.as<uint32_t>(), c->sorted.as<double>(),
+          c->st))
+      return -1;
+    c->launches += 6;
+  }
+  if (consumed) PSB_CUDA(cudaEventRecord(consumed, c->st));
+  if (c->memset_pending) { PSB_CUDA(cudaStreamWaitEvent(c->st, c->memset_pending, 0)); c->memset_pending = nullptr; }
+  const bool add = !(fresh && *fresh);
+  if (fresh) *fresh = false;
+  StageScope sc(c, PSB_T_ASSIGN, c->st);
+  if (launch_tile_accumulate(c->sorted.as<double>(), c->tile_start.as<uint32_t>(), g, scheme, precision, wscale,
+        wmax, add, m0, m1, c->st))
+    return -1;
+  c->launches++;
+  c->assign_path = 1;
+  return 0;
+}
+
 int sort_assign_chunk(psb_context *c, const double *src, size_t len, const AssignGeom &g,
     int scheme, int precision, double wscale, void *m0, void *m1, cudaEvent_t consumed,
-    bool bounds = false) {
+    bool bounds = false, bool *fresh = nullptr) {
   if (!len) return 0;
+  const bool tiles = c->opt_owner != 0 && tile_assign_supported(g) && len < ((size_t) 1 << 29) &&
+      (c->opt_owner > 0 || len >= (size_t) g.ng * g.ng * g.ng / 32);
+  if (tiles) {
+    double *partials = nullptr;
+    if (bounds) {
+      const int nblk = row_keys_blocks(len);
+      if (c->bounds_part.reserve_keep(c->bounds_used + sizeof(double) * 6 * nblk, c->bounds_used, c->st)) return -1;
+      partials = reinterpret_cast<double *>(c->bounds_part.as<char>() + c->bounds_used);
+      c->bounds_used += sizeof(double) * 6 * nblk;
+    }
+    return tile_assign_chunk(c, src, len, g, scheme, precision, wscale, m0, m1, consumed, partials, fresh);
+  }
+  if (zero_if_fresh(c, g, precision, m0, m1, fresh)) return -1;
+  c->assign_path = 0;
   const bool do_sort = c->opt_sort && len >= (size_t) c->opt_sort_min;
   double *partials = nullptr;
   if (bounds) {
@@ -339,10 +415,10 @@ int sort_assign_chunk(psb_context *c, const double *src, size_t len, const Assig
 const size_t DEV_CHUNK = (size_t) 1 << 28;      // particles per chunk (8.6 GB of records)
 
 int assign_catalog(psb_context *c, const double *dev, size_t n, const AssignGeom &g, int scheme,
-    int precision, double wscale, void *m0, void *m1, bool bounds) {
+    int precision, double wscale, void *m0, void *m1, bool bounds, bool *fresh) {
   for (size_t off = 0; off < n; off += DEV_CHUNK)
     if (sort_assign_chunk(c, dev + 4 * off, std::min(DEV_CHUNK, n - off), g, scheme, precision,
-          wscale, m0, m1, nullptr, bounds))
+          wscale, m0, m1, nullptr, bounds, fresh))
       return -1;
   return 0;
 }
@@ -457,7 +533,7 @@ std::vector<size_t> stream_schedule(const psb_context *c, size_t n) {
 }
 
 int stream_catalog(psb_context *c, const double *host, size_t n, const AssignGeom &g, int scheme,
-    int precision, double wscale, void *m0, void *m1) {
+    int precision, double wscale, void *m0, void *m1, bool *fresh) {
   if (!n) return 0;
   const std::vector<size_t> sched = stream_schedule(c, n);
   const size_t chunk_max = *std::max_element(sched.begin(), sched.end());
@@ -485,7 +561,7 @@ int stream_catalog(psb_context *c, const double *host, size_t n, const AssignGeo
     }
     PSB_CUDA(cudaEventRecord(c->ev_filled[s], c->st_copy));
     PSB_CUDA(cudaStreamWaitEvent(c->st, c->ev_filled[s], 0));
-    if (sort_assign_chunk(c, buf, len, g, scheme, precision, wscale, m0, m1, c->ev_consumed[s], true))
+    if (sort_assign_chunk(c, buf, len, g, scheme, precision, wscale, m0, m1, c->ev_consumed[s], true, fresh))
       return -1;
   }
   return 0;
@@ -1018,6 +1094,7 @@ void psb_destroy(psb_context *c) {
   }
   if (c->st_copy) cudaStreamDestroy(c->st_copy);
   c->fka.release(); c->sorted.release(); c->keys.release(); c->hist.release();
+  c->tile_cnt.release(); c->tile_start.release(); c->wmax_buf.release();
   c->cursor.release(); c->cubtmp.release(); c->bounds_part.release(); c->fftwork.release(); c->fftdone.release(); c->cnvt_tab.release();
   c->tables.release(); c->binscratch.release(); c->bins.release();
   reset_timings(c);
@@ -1038,6 +1115,7 @@ int psb_set_option(psb_context *c, const char *name, long value) {
   if (!strcmp(name, "sort_min")) { c->opt_sort_min = value; return 0; }
   if (!strcmp(name, "strip")) { c->opt_strip = value; return 0; }
   if (!strcmp(name, "coop")) { c->opt_coop = value; return 0; }
+  if (!strcmp(name, "owner")) { c->opt_owner = value; return 0; }
   if (!strcmp(name, "coop_variant")) { c->opt_coop_variant = value; return 0; }
   if (!strcmp(name, "xgroup")) { c->opt_xgroup = value; return 0; }
   if (!strcmp(name, "own_fft")) { c->opt_own_fft = value; return 0; }
@@ -1190,23 +1268,28 @@ int psb_mesh(psb_context *c, const psb_params *par, const psb_cats *cats) {
       PSB_CUDA(cudaEventRecord(c->ev_memset[i], c->st_aux));
     }
   }
+  // with the owner-computes assignment the first dense chunk STORES whole tiles, so the
+  // meshes are not zeroed up front: whoever touches a mesh first takes care of it
+  const bool lazy_zero = !c->opt_memset_overlap && c->opt_owner != 0 && tile_assign_supported(g);
   for (int i = 0; i < nc; i++) {
+    bool fresh = lazy_zero;
+    void *m0 = c->mesh[i][0].p, *m1 = par->intlace ? c->mesh[i][1].p : nullptr;
     if (c->opt_memset_overlap) c->memset_pending = c->ev_memset[i];
-    else
+    else if (!lazy_zero)
       for (int f = 0; f < nf; f++) {
         StageScope sc(c, PSB_T_MEMSET, c->st);
         PSB_CUDA(cudaMemsetAsync(c->mesh[i][f].p, 0, mesh_bytes, c->st));
       }
-    void *m0 = c->mesh[i][0].p, *m1 = par->intlace ? c->mesh[i][1].p : nullptr;
     if (streaming) {
-      if (stream_catalog(c, cats->data[i], cnt[i][0], g, par->assign, prec, 1.0, m0, m1)) return -1;
+      if (stream_catalog(c, cats->data[i], cnt[i][0], g, par->assign, prec, 1.0, m0, m1, &fresh)) return -1;
     }
     else {
-      if (assign_catalog(c, dptr[i][0], cnt[i][0], g, par->assign, prec, 1.0, m0, m1, deferred)) return -1;
+      if (assign_catalog(c, dptr[i][0], cnt[i][0], g, par->assign, prec, 1.0, m0, m1, deferred, &fresh)) return -1;
       if (!par->issim &&
-          assign_catalog(c, dptr[i][1], cnt[i][1], g, par->assign, prec, -cats->alpha[i], m0, m1))
+          assign_catalog(c, dptr[i][1], cnt[i][1], g, par->assign, prec, -cats->alpha[i], m0, m1, false, &fresh))
         return -1;
     }
+    if (zero_if_fresh(c, g, prec, m0, m1, &fresh)) return -1;      // empty catalogue
     // nothing was scattered (empty catalogue): later consumers still need the zeros
     if (c->memset_pending) { PSB_CUDA(cudaStreamWaitEvent(c->st, c->memset_pending, 0)); c->memset_pending = nullptr; }
     if (par->issim) {           // src/genr_mesh.c:904-909
@@ -1525,6 +1608,10 @@ long psb_launch_count(const psb_context *c) { return c ? c->launches : -1; }
 // the compute stream as a cudaStream_t (for hosts that want to record their own events on
 // it or order their own work after the library's)
 void *psb_stream(const psb_context *c) { return c ? (void *) c->st : nullptr; }
+
+// which scatter the last chunk of the last psb_mesh used: 0 = global reductions
+// (k_assign_coop), 1 = owner-computes tiles (k_tile_accumulate)
+int psb_assign_path(const psb_context *c) { return c ? c->assign_path : -1; }
 
 
 // ---------------------------------------------------------------------------

@@ -81,6 +81,8 @@ struct psb_context {
   cudaStream_t st_copy = nullptr;       // H2D engine stream of the streaming path
   cudaEvent_t ev_filled[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
   DevBuf sorted, keys, hist, cursor, cubtmp, bounds_part;
+  DevBuf tile_cnt, tile_start, wmax_buf;  // owner-computes assignment: list counts / offsets, max |w|
+  int assign_path = 0;                  // what the last scatter used: 0 global reductions, 1 owner-computes tiles
   size_t bounds_used = 0;               // bytes of bounds_part holding deferred bounds partials
   void *pinned[2] = {nullptr, nullptr};
   size_t pinned_bytes = 0;
@@ -113,6 +115,8 @@ struct psb_context {
   long opt_sort = 1;
   long opt_sort_min = 1 << 16;
   long opt_geom_sym = 1;                // fold +-n_x, +-n_y in the mode-counting pass
+  long opt_owner = -1;                  // owner-computes tile assignment: 1 / 0 / -1 = when the chunk is dense
+                                        // enough to pay for writing every mesh cell (>= Ntot / 32 particles)
   long opt_coop = 1;                    // z-coalesced scatter kernel
   long opt_coop_variant = 0;
   long opt_survey_direct = 1;           // survey l > 0: bin Fk0 x Fka_m directly (no Fkl field)
@@ -192,8 +196,10 @@ int check_params(const psb_params *p);
 int h2d_async(psb_context *c, void *dst, const void *src, size_t bytes, bool pinned,
     cudaStream_t stream);
 bool is_pinned(const void *p);
+// fresh (optional): *fresh says the meshes have not been initialised yet; the first
+// scatter then either stores whole tiles (owner-computes path) or zeroes them first
 int assign_catalog(psb_context *c, const double *dev, size_t n, const AssignGeom &g, int scheme,
-    int precision, double wscale, void *m0, void *m1, bool bounds = false);
+    int precision, double wscale, void *m0, void *m1, bool bounds = false, bool *fresh = nullptr);
 void normalise(psb_result *res, const psb_params *par, bool issim, int nc, const double *shot,
     const double *norm);
 bool same_bins(const psb_context *c, const psb_params *p);

@@ -58,6 +58,16 @@ int launch_row_scatter(const double *p, size_t n, const uint32_t *keys,
 // mesh1 may be null (no interlacing).  precision: 8 or 4.
 int launch_assign(const double *p, size_t n, const AssignGeom &g, int scheme,
     int precision, double wscale, void *mesh0, void *mesh1, cudaStream_t st);
+// owner-computes assignment (assign_tiles.cu): per-tile particle lists, fixed-point
+// accumulation in shared memory, one plain store per mesh cell
+bool tile_assign_supported(const AssignGeom &g);
+size_t tile_list_count(const AssignGeom &g);
+int launch_tile_count(const double *p, size_t n, const AssignGeom &g, int scheme, bool interlace,
+    uint32_t *cnt, double *partials, double *wmax_part, double *wmax, cudaStream_t st);
+int launch_tile_fill(const double *p, size_t n, const AssignGeom &g, int scheme, bool interlace,
+    uint32_t *cursor, double *lists, cudaStream_t st);
+int launch_tile_accumulate(const double *lists, const uint32_t *start, const AssignGeom &g, int scheme,
+    int precision, double wscale, const double *wmax, bool add, void *mesh0, void *mesh1, cudaStream_t st);
 int launch_unpad_copy(const void *mesh, void *dst, int ng, int rowlen,
     int precision, cudaStream_t st);
 int launch_owner_keys(const double *p, size_t n, const AssignGeom &g, int nranks,

@@ -76,11 +76,14 @@ def test_medium_random_configuration_against_oracle(seed, ctx, port_oracle):
     data = cats if len(cats) > 1 else cats[0]
     want = port_oracle.run(data, keep_mesh=True, **kw)
     got = powspec_b200.run(data, ctx=ctx, keep_mesh=True, **kw)
+    # dense catalogues take the owner-computes assignment, whose fixed-point contributions
+    # are rounded to ~1e-12 of the cell values (csrc/assign_tiles.cu)
+    mesh_tol = 1e-12 if ctx.L.psb_assign_path(ctx.h) == 0 else 1e-10
     for i in range(len(cats)):
         scale = np.abs(want.Fr[i]).max()
-        assert np.abs(got.Fr[i] - want.Fr[i]).max() < 1e-12 * scale, f"medium fuzz {seed}: mesh {i}"
+        assert np.abs(got.Fr[i] - want.Fr[i]).max() < mesh_tol * scale, f"medium fuzz {seed}: mesh {i}"
         if kw["interlace"]:
-            assert np.abs(got.Frl[i] - want.Frl[i]).max() < 1e-12 * scale, f"medium fuzz {seed}: shifted mesh {i}"
+            assert np.abs(got.Frl[i] - want.Frl[i]).max() < mesh_tol * scale, f"medium fuzz {seed}: shifted mesh {i}"
     worst = assert_spectra_close(got, want, TOL_DOUBLE, f"medium fuzz {seed}: {kw}",
                                  abs_floor=noise_floor(want, kw["poles"]))
     print(f"medium fuzz {seed}: worst rel err {worst:.2e}")

@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) k_tiles(const double2 *__restrict__ p, si
           if (tz < 0) continue;
           const unsigned tile = ((unsigned) tx * g.nty + ty) * g.ntz + tz;
           const unsigned pos = atomicAdd(cnt_or_cursor + tile, 1u);
-          if (FILL) { out[2 * (size_t) pos] = a; out[2 * (size_t) pos + 1] = b; }
+          if (FILL) asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" :: "l"(out + 2 * (size_t) pos), "d"(a.x), "d"(a.y), "d"(b.x), "d"(b.y) : "memory");
         }
       }
     }
