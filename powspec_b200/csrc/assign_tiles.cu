@@ -158,14 +158,6 @@ __global__ void k_wmax_reduce(const double *__restrict__ part, int nblk, double 
   if (threadIdx.x == 0) *wmax = v;
 }
 
-// predicated shared-memory reductions (no branch around the adds of an update) into both
-// limbs of one cell: low limb at addr, high limb 4 TCELLS bytes further (immediate offset)
-__device__ __forceinline__ void red_shared2(uint32_t addr, uint32_t lo, uint32_t hi, bool on) {
-  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %3, 0;\n\t@q red.shared.add.u32 [%0], %1;\n\t"
-      "@q red.shared.add.u32 [%0+%4], %2;\n\t}"
-      :: "r"(addr), "r"(lo), "r"(hi), "r"((uint32_t) on), "n"(4 * TCELLS) : "memory");
-}
-
 // round(v) as a 52-bit two's complement integer by the 1.5 * 2^52 magic add (mantissa
 // field = 2^51 + round(v)): low limb = bits 0..LOBITS-1 (>= 0), high limb = the signed rest
 __device__ __forceinline__ void split_fixed(double v, uint32_t &lo, uint32_t &hi) {
@@ -175,13 +167,102 @@ __device__ __forceinline__ void split_fixed(double v, uint32_t &lo, uint32_t &hi
   hi = (uint32_t) ((int) (((hw ^ 0x80000u) << 12) | ((lw >> LOBITS) << (LOBITS - 20))) >> (LOBITS - 20));
 }
 
+// one row of the stencil, all z cells inside the tile (consecutive): no predicates
+template <int OFF>
+__device__ __forceinline__ void red_pair(uint32_t addr, uint32_t lo, uint32_t hi) {
+  asm volatile("red.shared.add.u32 [%0+%3], %1;\n\tred.shared.add.u32 [%0+%4], %2;"
+      :: "r"(addr), "r"(lo), "r"(hi), "n"(OFF), "n"(OFF + 4 * TCELLS) : "memory");
+}
+template <int C, int NS>
+__device__ __forceinline__ void row_inside(uint32_t addr, double wxy, const double (&wz)[NS]) {
+  if constexpr (C < NS) {
+    uint32_t lo, hi;
+    split_fixed(wxy * wz[C], lo, hi);
+    red_pair<4 * C>(addr, lo, hi);
+    row_inside<C + 1, NS>(addr, wxy, wz);
+  }
+}
+
+// Adds the in-tile part of one listed particle's stencil.  PARTIAL = false: the common
+// case, all z cells inside the tile, straight-line code; returns true (nothing added) if
+// only some of them are, and the caller queues the particle for a PARTIAL = true pass —
+// so that the predicated (branchy) code runs on full warps of such particles instead of
+// being dragged through every warp by one lane.
+template <int SCHEME, bool PARTIAL>
+__device__ __forceinline__ bool tile_add(const double2 *__restrict__ parts, size_t idx, int f,
+    const AssignGeom &g, double wscale, double norm, int x0, int y0, int z0, uint32_t sm_lo) {
+  constexpr int NS = SCHEME + 1;
+  double2 a, b;
+  ld_record(parts, idx, a, b);
+  double x[3] = {a.x, a.y, b.x};
+  const double *org = f ? g.sorg : g.org;
+  if (f) {
+    // shift_cat, src/genr_mesh.c:595-600: periodic wrap into the shifted box
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+      if (x[k] >= __dadd_rn(g.sorg[k], g.len[k])) x[k] = __dsub_rn(x[k], g.len[k]);
+  }
+  int ix[NS], iy[NS], iz[NS], cc;
+  double wx[NS], wy[NS], wz[NS], dd;
+  const double ngd = (double) g.ng;
+  grid_split(x[2], AxisXform{org[2], ngd, g.len[2], g.inv_len[2]}, cc, dd);
+  stencil_from<SCHEME>(cc, dd, g.ng, iz, wz);
+  bool zin[NS];
+  uint32_t lz[NS];
+  int nin = 0;
+#pragma unroll
+  for (int c = 0; c < NS; c++) {
+    lz[c] = (uint32_t) (iz[c] - z0);
+    zin[c] = lz[c] < (uint32_t) TZ;
+    nin += zin[c];
+  }
+  if (nin == 0) return false;
+  // the straight-line path takes the z cells as consecutive: all inside the tile and no
+  // periodic wrap among them (a tile that spans the whole axis holds both ends)
+  if (!PARTIAL && (nin < NS || lz[NS - 1] != lz[0] + (uint32_t) (NS - 1))) return true;
+  grid_split(x[0], AxisXform{org[0], ngd, g.len[0], g.inv_len[0]}, cc, dd);
+  stencil_from<SCHEME>(cc, dd, g.ng, ix, wx);
+  grid_split(x[1], AxisXform{org[1], ngd, g.len[1], g.inv_len[1]}, cc, dd);
+  stencil_from<SCHEME>(cc, dd, g.ng, iy, wy);
+  // the particle weight enters through the x weights (src/genr_mesh.c:110-111, 175-177);
+  // PCS folds 1/216 into it (:274-278); then the fixed-point scale
+  double pw = b.y * wscale;
+  if constexpr (SCHEME == 3) pw *= 0x1.2f684bda12f68p-8;
+#pragma unroll
+  for (int q = 0; q < NS; q++) wx[q] = (wx[q] * pw) * norm;
+#pragma unroll
+  for (int u = 0; u < NS; u++) {
+    const uint32_t lx = (uint32_t) (ix[u] - x0);
+    if (lx >= (uint32_t) TX) continue;
+#pragma unroll
+    for (int v = 0; v < NS; v++) {
+      const uint32_t ly = (uint32_t) (iy[v] - y0);
+      if (ly >= (uint32_t) TY) continue;
+      const double wxy = wx[u] * wy[v];
+      const uint32_t row = sm_lo + ((lx * TY + ly) * TZ) * 4u;
+      if constexpr (!PARTIAL) row_inside<0, NS>(row + lz[0] * 4u, wxy, wz);
+      else {
+#pragma unroll
+        for (int c = 0; c < NS; c++) {
+          if (!zin[c]) continue;
+          uint32_t lo, hi;
+          split_fixed(wxy * wz[c], lo, hi);
+          red_pair<0>(row + lz[c] * 4u, lo, hi);
+        }
+      }
+    }
+  }
+  return false;
+}
+
 // MODE 0: the tile is stored (the mesh need not be initialised); 1: added to the mesh
 template <int SCHEME, typename real, int NFIELD, int MODE>
 __global__ void __launch_bounds__(ACC_THREADS, 2) k_tile_accumulate(const double2 *__restrict__ parts,
     const uint32_t *__restrict__ start, AssignGeom g, double wscale, const double *__restrict__ wmax_dev,
     real *__restrict__ mesh0, real *__restrict__ mesh1) {
-  constexpr int NS = SCHEME + 1;
   extern __shared__ uint32_t sm[];              // lo[TCELLS] | hi[TCELLS]
+  __shared__ uint32_t queue[BATCH];             // listed particles that straddle the tile's z faces
+  __shared__ uint32_t nqueue;
   const uint32_t sm_lo = (uint32_t) __cvta_generic_to_shared(sm);
   const TileDims td = tile_dims(g.ng);
   const uint32_t nwork = (uint32_t) NFIELD * (uint32_t) (td.ntx * td.nty * td.ntz);
@@ -189,6 +270,7 @@ __global__ void __launch_bounds__(ACC_THREADS, 2) k_tile_accumulate(const double
   // times 1/216)
   const double wbound = *wmax_dev * fabs(wscale);
   for (int i = threadIdx.x; i < 2 * TCELLS; i += ACC_THREADS) sm[i] = 0;
+  if (threadIdx.x == 0) nqueue = 0;
   __syncthreads();
   for (uint32_t work = blockIdx.x; work < nwork; work += gridDim.x) {
     const uint32_t tile = work / NFIELD;
@@ -201,64 +283,17 @@ __global__ void __launch_bounds__(ACC_THREADS, 2) k_tile_accumulate(const double
     int S = 44;
     for (uint32_t q = 1u << (31 - (44 - LOBITS)); q < np && S > 24; q <<= 1) S--;
     const double norm = wbound > 0.0 ? ldexp(1.0, S) / wbound : 0.0;
-    const double *org = f ? g.sorg : g.org;
     for (uint32_t base = 0; base < np; base += BATCH) {
       const uint32_t lim = min(np, base + BATCH);
-      for (uint32_t j = base + threadIdx.x; j < lim; j += ACC_THREADS) {
-        double2 a, b;
-        ld_record(parts, (size_t) b0 + j, a, b);
-        double x[3] = {a.x, a.y, b.x};
-        if (f) {
-          // shift_cat, src/genr_mesh.c:595-600: periodic wrap into the shifted box
-#pragma unroll
-          for (int k = 0; k < 3; k++)
-            if (x[k] >= __dadd_rn(g.sorg[k], g.len[k])) x[k] = __dsub_rn(x[k], g.len[k]);
-        }
-        int ix[NS], iy[NS], iz[NS], cc;
-        double wx[NS], wy[NS], wz[NS], dd;
-        const double ngd = (double) g.ng;
-        grid_split(x[2], AxisXform{org[2], ngd, g.len[2], g.inv_len[2]}, cc, dd);
-        stencil_from<SCHEME>(cc, dd, g.ng, iz, wz);
-        bool zin[NS], anyz = false;
-        uint32_t offz[NS];          // byte offset of the z cell inside its row (0 if outside: masked)
-#pragma unroll
-        for (int c = 0; c < NS; c++) {
-          const uint32_t lz = (uint32_t) (iz[c] - z0);
-          zin[c] = lz < (uint32_t) TZ;
-          offz[c] = zin[c] ? lz * 4u : 0u;
-          anyz |= zin[c];
-        }
-        if (!anyz) continue;
-        grid_split(x[0], AxisXform{org[0], ngd, g.len[0], g.inv_len[0]}, cc, dd);
-        stencil_from<SCHEME>(cc, dd, g.ng, ix, wx);
-        grid_split(x[1], AxisXform{org[1], ngd, g.len[1], g.inv_len[1]}, cc, dd);
-        stencil_from<SCHEME>(cc, dd, g.ng, iy, wy);
-        // the particle weight enters through the x weights (src/genr_mesh.c:110-111,
-        // 175-177); PCS folds 1/216 into it (:274-278); then the fixed-point scale
-        double pw = b.y * wscale;
-        if constexpr (SCHEME == 3) pw *= 0x1.2f684bda12f68p-8;
-#pragma unroll
-        for (int q = 0; q < NS; q++) wx[q] = (wx[q] * pw) * norm;
-#pragma unroll
-        for (int u = 0; u < NS; u++) {
-          const uint32_t lx = (uint32_t) (ix[u] - x0);
-          if (lx >= (uint32_t) TX) continue;
-#pragma unroll
-          for (int v = 0; v < NS; v++) {
-            const uint32_t ly = (uint32_t) (iy[v] - y0);
-            if (ly >= (uint32_t) TY) continue;
-            const double wxy = wx[u] * wy[v];
-            const uint32_t row = sm_lo + ((lx * TY + ly) * TZ) * 4u;
-#pragma unroll
-            for (int c = 0; c < NS; c++) {
-              uint32_t lo, hi;
-              split_fixed(wxy * wz[c], lo, hi);
-              red_shared2(row + offz[c], lo, hi, zin[c]);
-            }
-          }
-        }
-      }
+      for (uint32_t j = base + threadIdx.x; j < lim; j += ACC_THREADS)
+        if (tile_add<SCHEME, false>(parts, (size_t) b0 + j, f, g, wscale, norm, x0, y0, z0, sm_lo))
+          queue[atomicAdd(&nqueue, 1u)] = j;
       __syncthreads();
+      const uint32_t nq = nqueue;
+      for (uint32_t k = threadIdx.x; k < nq; k += ACC_THREADS)
+        tile_add<SCHEME, true>(parts, (size_t) b0 + queue[k], f, g, wscale, norm, x0, y0, z0, sm_lo);
+      __syncthreads();
+      if (threadIdx.x == 0) nqueue = 0;
       if (lim < np) {
         // fold the carries so that neither limb can wrap in the next batch
         for (int i = threadIdx.x; i < TCELLS; i += ACC_THREADS) {
