@@ -9,15 +9,22 @@
 //      particle's stencil with the native shared-memory ATOMS.ADD — the only shared atomic
 //      add that is not a compare-and-swap loop on this part (2.4 T adds/s against 0.47 T/s
 //      for fp64, tools/smem_atomic_probe.cu);
-//   3. the tile is converted back and written ONCE with plain coalesced stores: no memset
-//      of the mesh, no read-modify-write, no global atomics.  DRAM traffic of the stage:
-//      particles + lists + one write of the mesh (profiles/README.md).
+//   3. the tile is converted back IN PLACE (the two limbs of a cell are the 8 bytes of its
+//      double) and written ONCE: double-precision meshes by one TMA tensor store per tile
+//      (cp.async.bulk.tensor.3d, UTMASTG; the hardware clips partial tiles), the other
+//      cases by 16-byte stores.  No memset of the mesh, no read-modify-write, no global
+//      atomics.  DRAM traffic of the stage: particles + lists + one write of the mesh
+//      (profiles/README.md).
+//
+// The lists only have to be SUPERSETS: count / fill use a cheap conservative cell range
+// (one multiply per axis, 1e-6 of a cell of slack), the accumulation recomputes every
+// stencil with the reference's arithmetic and drops what is outside its tile.
 //
 // Fixed point: a contribution v = w wx wy wz is scaled by 2^S / max|w| and rounded to an
-// integer (S = 44 for tiles of up to 256 listed particles, one bit less for every
-// doubling: the high limb must hold the sum); low limb = 21 bits, so 2048 adds fit before
-// the carries are folded (once per 2048 listed particles).  Rounding error per
-// contribution <= 2^-(S+1) max|w| (2.3e-13 for a typical tile of BASELINE config 2): far
+// integer (S = 43 for tiles of fewer than 256 listed particles, one bit less for every
+// doubling: the high limb must hold the sum below 2^30); low limb = 21 bits, so 2048 adds
+// fit before the carries are folded (once per 2048 listed particles).  Rounding error per
+// contribution <= 2^-(S+1) max|w| (4.5e-13 for a typical tile of BASELINE config 2): far
 // inside the 1e-6 budget of P_ell(k), and — integer addition being associative — the
 // mesh is bit-for-bit reproducible from run to run, which the global-reduction scatter
 // is not.
@@ -28,7 +35,10 @@
 
 #include "assign_common.cuh"
 
+#include <cuda.h>      // CUtensorMap (types only: the encoder is looked up at run time)
+
 #include <cfloat>
+#include <cstring>
 
 namespace psb {
 
@@ -47,29 +57,25 @@ __host__ __device__ inline TileDims tile_dims(int ng) {
   return {(ng + TX - 1) / TX, (ng + TY - 1) / TY, (ng + TZ - 1) / TZ};
 }
 
-// the (periodic) cell range [lo, lo + cnt) that the stencils of all fields reach along
-// one axis
+// A SUPERSET of the (periodic) cell range [lo, lo + cnt) that the stencils of all fields
+// reach along one axis.  With t the grid coordinate and c = floor(t) the first cell is
+// floor(t + A) - B (NGP: the nearest cell; CIC: c; TSC: the nearest cell - 1; PCS: c - 1,
+// src/genr_mesh.c:60-66, 98-108, 157-167, 259-261) and the half-cell shifted field sees
+// t + 1/2 (shift_cat, :590-602).  t is taken as (x - org) * (Ng / L), within 1e-11 of the
+// reference's rounding of (x - org) * Ng / L; EPS covers that, so the exact stencil of the
+// accumulation pass always lies inside the range.
 template <int SCHEME, bool INTERLACE>
-__device__ __forceinline__ void axis_reach(double x, double org, double sorg, double len, double inv_len,
-    int ng, int &lo, int &cnt) {
-  constexpr int NS = SCHEME + 1;
-  int i0[NS], c;
-  double w0[NS], d;
-  grid_split(x, AxisXform{org, (double) ng, len, inv_len}, c, d);
-  stencil_from<SCHEME>(c, d, ng, i0, w0);
-  lo = i0[0];
-  cnt = NS;
-  if constexpr (INTERLACE) {
-    // shift_cat, src/genr_mesh.c:595-600
-    if (x >= __dadd_rn(sorg, len)) x = __dsub_rn(x, len);
-    int i1[NS];
-    grid_split(x, AxisXform{sorg, (double) ng, len, inv_len}, c, d);
-    stencil_from<SCHEME>(c, d, ng, i1, w0);
-    int dd = i1[0] - lo;
-    if (dd < 0) dd += ng;
-    if (dd <= NS) cnt = dd + NS;                // the shifted stencil starts dd cells higher
-    else { lo = i1[0]; cnt = (ng - dd) + NS; }  // ... or ng - dd cells lower
-  }
+__device__ __forceinline__ void axis_reach(double x, double org, double scale, int ng, int &lo, int &cnt) {
+  constexpr double A = (SCHEME == 0 || SCHEME == 2) ? 0.5 : 0.0;
+  constexpr int B = (SCHEME >= 2) ? 1 : 0;
+  constexpr double EPS = 1e-6;
+  const double t = (x - org) * scale;
+  int first = __double2int_rd(t + (A - EPS)) - B;
+  const int last = __double2int_rd(t + (A + (INTERLACE ? 0.5 : 0.0) + EPS)) - B + SCHEME;
+  cnt = min(max(last - first + 1, 1), SCHEME + 3);
+  if (first < 0) first += ng;
+  if (first >= ng) first -= ng;
+  lo = min(max(first, 0), ng - 1);              // coordinates outside the box: stay in bounds
 }
 
 // tiles overlapped along one axis: the first cell's and, if different, the last cell's
@@ -82,47 +88,87 @@ __device__ __forceinline__ void axis_tiles(int lo, int cnt, int T, int ng, int &
   if (t1 == t0) t1 = -1;
 }
 
+struct TileSet {
+  uint32_t first;       // the tile of the lowest cells: every particle has it
+  uint32_t step[3];     // distance to the second tile along x, y, z (0: none)
+};
+
+template <int SCHEME, bool INTERLACE>
+__device__ __forceinline__ TileSet tile_set(double2 a, double2 b, const AssignGeom &g, const double (&scale)[3],
+    const TileDims &td) {
+  int lo[3], cnt[3], t0[3], t1[3];
+  axis_reach<SCHEME, INTERLACE>(a.x, g.org[0], scale[0], g.ng, lo[0], cnt[0]);
+  axis_reach<SCHEME, INTERLACE>(a.y, g.org[1], scale[1], g.ng, lo[1], cnt[1]);
+  axis_reach<SCHEME, INTERLACE>(b.x, g.org[2], scale[2], g.ng, lo[2], cnt[2]);
+  axis_tiles(lo[0], cnt[0], TX, g.ng, t0[0], t1[0]);
+  axis_tiles(lo[1], cnt[1], TY, g.ng, t0[1], t1[1]);
+  axis_tiles(lo[2], cnt[2], TZ, g.ng, t0[2], t1[2]);
+  TileSet ts;
+  ts.first = ((uint32_t) t0[0] * td.nty + t0[1]) * td.ntz + t0[2];
+  // unsigned wrap-around differences: first + step is the neighbour's index
+  ts.step[0] = t1[0] < 0 ? 0u : (uint32_t) (t1[0] - t0[0]) * (uint32_t) (td.nty * td.ntz);
+  ts.step[1] = t1[1] < 0 ? 0u : (uint32_t) (t1[1] - t0[1]) * (uint32_t) td.ntz;
+  ts.step[2] = t1[2] < 0 ? 0u : (uint32_t) (t1[2] - t0[2]);
+  return ts;
+}
+
+// the up to seven further tiles of a particle that straddles tile faces
+template <bool FILL>
+__device__ __forceinline__ void tile_extra(const TileSet &ts, uint32_t *__restrict__ cnt_or_cursor,
+    double2 *__restrict__ out, double2 a, double2 b) {
+#pragma unroll
+  for (int m = 1; m < 8; m++) {
+    if (((m & 1) && !ts.step[2]) || ((m & 2) && !ts.step[1]) || ((m & 4) && !ts.step[0])) continue;
+    const uint32_t tile = ts.first + ((m & 1) ? ts.step[2] : 0u) + ((m & 2) ? ts.step[1] : 0u) +
+        ((m & 4) ? ts.step[0] : 0u);
+    const uint32_t pos = atomicAdd(cnt_or_cursor + tile, 1u);
+    if (FILL) st_record(out, pos, a, b);
+  }
+}
+
 // FILL = false: count the list lengths (and, optionally, the coordinate bounds and the
-// largest |weight| of the block's particles); FILL = true: write the records
-template <int SCHEME, bool INTERLACE, bool FILL>
+// largest |weight| of the block's particles); FILL = true: write the records.  The fill
+// pass waits for the returned list positions: UNROLL particles per thread are in flight.
+template <int SCHEME, bool INTERLACE, bool FILL, int UNROLL>
 __global__ void __launch_bounds__(256) k_tile_lists(const double2 *__restrict__ p, size_t n, AssignGeom g,
     uint32_t *__restrict__ cnt_or_cursor, double2 *__restrict__ out, double *__restrict__ partials,
     double *__restrict__ wmax_part) {
   const TileDims td = tile_dims(g.ng);
+  const double scale[3] = {(double) g.ng / g.len[0], (double) g.ng / g.len[1], (double) g.ng / g.len[2]};
   double lo3[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi3[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX}, wm = 0.0;
-  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
-    double2 a, b;
-    ld_record(p, i, a, b);
-    if (!FILL) {
-      lo3[0] = fmin(lo3[0], a.x); hi3[0] = fmax(hi3[0], a.x);
-      lo3[1] = fmin(lo3[1], a.y); hi3[1] = fmax(hi3[1], a.y);
-      lo3[2] = fmin(lo3[2], b.x); hi3[2] = fmax(hi3[2], b.x);
-      wm = fmax(wm, fabs(b.y));
+  const size_t stride = (size_t) gridDim.x * blockDim.x;
+  for (size_t i0 = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i0 < n; i0 += stride * UNROLL) {
+    double2 a[UNROLL], b[UNROLL];
+    TileSet ts[UNROLL];
+    uint32_t pos[UNROLL];
+    bool more = false;
+#pragma unroll
+    for (int u = 0; u < UNROLL; u++) {
+      const size_t i = i0 + u * stride;
+      if (i < n) ld_record(p, i, a[u], b[u]);
     }
-    int lo[3], cnt[3], t0[3], t1[3];
-    axis_reach<SCHEME, INTERLACE>(a.x, g.org[0], g.sorg[0], g.len[0], g.inv_len[0], g.ng, lo[0], cnt[0]);
-    axis_reach<SCHEME, INTERLACE>(a.y, g.org[1], g.sorg[1], g.len[1], g.inv_len[1], g.ng, lo[1], cnt[1]);
-    axis_reach<SCHEME, INTERLACE>(b.x, g.org[2], g.sorg[2], g.len[2], g.inv_len[2], g.ng, lo[2], cnt[2]);
-    axis_tiles(lo[0], cnt[0], TX, g.ng, t0[0], t1[0]);
-    axis_tiles(lo[1], cnt[1], TY, g.ng, t0[1], t1[1]);
-    axis_tiles(lo[2], cnt[2], TZ, g.ng, t0[2], t1[2]);
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
-      const int tx = u ? t1[0] : t0[0];
-      if (tx < 0) continue;
-#pragma unroll
-      for (int v = 0; v < 2; v++) {
-        const int ty = v ? t1[1] : t0[1];
-        if (ty < 0) continue;
-#pragma unroll
-        for (int s = 0; s < 2; s++) {
-          const int tz = s ? t1[2] : t0[2];
-          if (tz < 0) continue;
-          const uint32_t tile = ((uint32_t) tx * td.nty + ty) * td.ntz + tz;
-          const uint32_t pos = atomicAdd(cnt_or_cursor + tile, 1u);
-          if (FILL) st_record(out, pos, a, b);
-        }
+    for (int u = 0; u < UNROLL; u++) {
+      if (i0 + u * stride >= n) continue;
+      if (!FILL) {
+        lo3[0] = fmin(lo3[0], a[u].x); hi3[0] = fmax(hi3[0], a[u].x);
+        lo3[1] = fmin(lo3[1], a[u].y); hi3[1] = fmax(hi3[1], a[u].y);
+        lo3[2] = fmin(lo3[2], b[u].x); hi3[2] = fmax(hi3[2], b[u].x);
+        wm = fmax(wm, fabs(b[u].y));
       }
+      ts[u] = tile_set<SCHEME, INTERLACE>(a[u], b[u], g, scale, td);
+      pos[u] = atomicAdd(cnt_or_cursor + ts[u].first, 1u);
+      more |= (ts[u].step[0] | ts[u].step[1] | ts[u].step[2]) != 0u;
+    }
+    if (FILL) {
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++)
+        if (i0 + u * stride < n) st_record(out, pos[u], a[u], b[u]);
+    }
+    if (more) {
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++)
+        if (i0 + u * stride < n) tile_extra<FILL>(ts[u], cnt_or_cursor, out, a[u], b[u]);
     }
   }
   if (FILL) return;
@@ -158,28 +204,58 @@ __global__ void k_wmax_reduce(const double *__restrict__ part, int nblk, double 
   if (threadIdx.x == 0) *wmax = v;
 }
 
-// round(v) as a 52-bit two's complement integer by the 1.5 * 2^52 magic add (mantissa
-// field = 2^51 + round(v)): low limb = bits 0..LOBITS-1 (>= 0), high limb = the signed rest
+// Shared-memory cell: {low limb, high limb}, 8 bytes — the place of the cell's double in
+// the flushed tile.
+//
+// round(v) (|v| < 2^51) by the 1.5 * 2^52 magic add: the mantissa field is 2^51 + round(v),
+// so the low limb is its low LOBITS bits and the high limb (the signed rest) is bits
+// 21..52 of the pattern, whose two top bits (exponent LSB, the 2^51 offset) are cancelled
+// by adding 2^30 modulo 2^32.
 __device__ __forceinline__ void split_fixed(double v, uint32_t &lo, uint32_t &hi) {
   const double m = v + 6755399441055744.0;
   const uint32_t lw = (uint32_t) __double2loint(m), hw = (uint32_t) __double2hiint(m);
   lo = lw & LOMASK;
-  hi = (uint32_t) ((int) (((hw ^ 0x80000u) << 12) | ((lw >> LOBITS) << (LOBITS - 20))) >> (LOBITS - 20));
+  hi = __funnelshift_r(lw, hw, LOBITS) + 0x40000000u;
+}
+
+// the inverse: hi * 2^LOBITS + lo as a double, |value| < 2^51, without the conversion pipe
+__device__ __forceinline__ double join_fixed(uint32_t lo, uint32_t hi) {
+  const long long x = (long long) (int) hi * (long long) (1u << LOBITS) + (long long) lo;
+  return __longlong_as_double(x + 0x4338000000000000ll) - 6755399441055744.0;
 }
 
 // one row of the stencil, all z cells inside the tile (consecutive): no predicates
 template <int OFF>
 __device__ __forceinline__ void red_pair(uint32_t addr, uint32_t lo, uint32_t hi) {
   asm volatile("red.shared.add.u32 [%0+%3], %1;\n\tred.shared.add.u32 [%0+%4], %2;"
-      :: "r"(addr), "r"(lo), "r"(hi), "n"(OFF), "n"(OFF + 4 * TCELLS) : "memory");
+      :: "r"(addr), "r"(lo), "r"(hi), "n"(OFF), "n"(OFF + 4) : "memory");
 }
 template <int C, int NS>
 __device__ __forceinline__ void row_inside(uint32_t addr, double wxy, const double (&wz)[NS]) {
   if constexpr (C < NS) {
     uint32_t lo, hi;
     split_fixed(wxy * wz[C], lo, hi);
-    red_pair<4 * C>(addr, lo, hi);
+    red_pair<8 * C>(addr, lo, hi);
     row_inside<C + 1, NS>(addr, wxy, wz);
+  }
+}
+
+// does the fraction decide nothing?  (grid_split's test, two comparisons folded into one)
+__device__ __forceinline__ bool frac_is_safe(double d) {
+  return fabs(fabs(d - 0.5) - 0.25) < 0.25 - 1e-9;
+}
+
+// grid_split (assign_common.cuh) with the three comparisons on the fraction folded
+__device__ __forceinline__ void grid_split2(double x, const AxisXform &ax, int &c, double &d) {
+  const double a = __dmul_rn(__dsub_rn(x, ax.org), ax.ng);
+  const double q0 = a * ax.inv_len;
+  const double e = __fma_rn(-q0, ax.len, a);
+  double t = __fma_rn(e, ax.inv_len, q0);
+  split_floor(t, c, d);
+  if (!frac_is_safe(d)) {
+    t = __ddiv_rn(a, ax.len);                   // the reference's own arithmetic
+    c = (int) t;
+    d = t - (double) c;
   }
 }
 
@@ -190,7 +266,7 @@ __device__ __forceinline__ void row_inside(uint32_t addr, double wxy, const doub
 // being dragged through every warp by one lane.
 template <int SCHEME, bool PARTIAL>
 __device__ __forceinline__ bool tile_add(const double2 *__restrict__ parts, size_t idx, int f,
-    const AssignGeom &g, double wscale, double norm, int x0, int y0, int z0, uint32_t sm_lo) {
+    const AssignGeom &g, double wnorm, int x0, int y0, int z0, uint32_t sm_lo) {
   constexpr int NS = SCHEME + 1;
   double2 a, b;
   ld_record(parts, idx, a, b);
@@ -205,7 +281,7 @@ __device__ __forceinline__ bool tile_add(const double2 *__restrict__ parts, size
   int ix[NS], iy[NS], iz[NS], cc;
   double wx[NS], wy[NS], wz[NS], dd;
   const double ngd = (double) g.ng;
-  grid_split(x[2], AxisXform{org[2], ngd, g.len[2], g.inv_len[2]}, cc, dd);
+  grid_split2(x[2], AxisXform{org[2], ngd, g.len[2], g.inv_len[2]}, cc, dd);
   stencil_from<SCHEME>(cc, dd, g.ng, iz, wz);
   bool zin[NS];
   uint32_t lz[NS];
@@ -220,34 +296,34 @@ __device__ __forceinline__ bool tile_add(const double2 *__restrict__ parts, size
   // the straight-line path takes the z cells as consecutive: all inside the tile and no
   // periodic wrap among them (a tile that spans the whole axis holds both ends)
   if (!PARTIAL && (nin < NS || lz[NS - 1] != lz[0] + (uint32_t) (NS - 1))) return true;
-  grid_split(x[0], AxisXform{org[0], ngd, g.len[0], g.inv_len[0]}, cc, dd);
+  grid_split2(x[0], AxisXform{org[0], ngd, g.len[0], g.inv_len[0]}, cc, dd);
   stencil_from<SCHEME>(cc, dd, g.ng, ix, wx);
-  grid_split(x[1], AxisXform{org[1], ngd, g.len[1], g.inv_len[1]}, cc, dd);
+  grid_split2(x[1], AxisXform{org[1], ngd, g.len[1], g.inv_len[1]}, cc, dd);
   stencil_from<SCHEME>(cc, dd, g.ng, iy, wy);
   // the particle weight enters through the x weights (src/genr_mesh.c:110-111, 175-177);
-  // PCS folds 1/216 into it (:274-278); then the fixed-point scale
-  double pw = b.y * wscale;
-  if constexpr (SCHEME == 3) pw *= 0x1.2f684bda12f68p-8;
+  // wnorm = catalogue scale x fixed-point scale (x 1/216 for PCS, :274-278)
+  const double pw = b.y * wnorm;
 #pragma unroll
-  for (int q = 0; q < NS; q++) wx[q] = (wx[q] * pw) * norm;
+  for (int q = 0; q < NS; q++) wx[q] *= pw;
 #pragma unroll
   for (int u = 0; u < NS; u++) {
     const uint32_t lx = (uint32_t) (ix[u] - x0);
     if (lx >= (uint32_t) TX) continue;
+    const uint32_t xrow = sm_lo + lx * (uint32_t) (TY * TZ * 8) + (PARTIAL ? 0u : lz[0] * 8u);
 #pragma unroll
     for (int v = 0; v < NS; v++) {
       const uint32_t ly = (uint32_t) (iy[v] - y0);
       if (ly >= (uint32_t) TY) continue;
       const double wxy = wx[u] * wy[v];
-      const uint32_t row = sm_lo + ((lx * TY + ly) * TZ) * 4u;
-      if constexpr (!PARTIAL) row_inside<0, NS>(row + lz[0] * 4u, wxy, wz);
+      const uint32_t row = xrow + ly * (uint32_t) (TZ * 8);
+      if constexpr (!PARTIAL) row_inside<0, NS>(row, wxy, wz);
       else {
 #pragma unroll
         for (int c = 0; c < NS; c++) {
           if (!zin[c]) continue;
           uint32_t lo, hi;
           split_fixed(wxy * wz[c], lo, hi);
-          red_pair<0>(row + lz[c] * 4u, lo, hi);
+          red_pair<0>(row + lz[c] * 8u, lo, hi);
         }
       }
     }
@@ -255,111 +331,207 @@ __device__ __forceinline__ bool tile_add(const double2 *__restrict__ parts, size
   return false;
 }
 
-// MODE 0: the tile is stored (the mesh need not be initialised); 1: added to the mesh
-template <int SCHEME, typename real, int NFIELD, int MODE>
+struct TileMaps { CUtensorMap m[2]; };
+
+// MODE 0: the tile is stored (the mesh need not be initialised); 1: added to the mesh.
+// TMA: the flush of a double-precision tile is one bulk tensor store.
+template <int SCHEME, typename real, int NFIELD, int MODE, bool TMA>
 __global__ void __launch_bounds__(ACC_THREADS, 2) k_tile_accumulate(const double2 *__restrict__ parts,
     const uint32_t *__restrict__ start, AssignGeom g, double wscale, const double *__restrict__ wmax_dev,
-    real *__restrict__ mesh0, real *__restrict__ mesh1) {
-  extern __shared__ uint32_t sm[];              // lo[TCELLS] | hi[TCELLS]
+    real *__restrict__ mesh0, real *__restrict__ mesh1, const __grid_constant__ TileMaps maps) {
+  extern __shared__ __align__(1024) uint32_t sm[];      // cell c: sm[2c] low limb, sm[2c + 1] high limb
   __shared__ uint32_t queue[BATCH];             // listed particles that straddle the tile's z faces
   __shared__ uint32_t nqueue;
   const uint32_t sm_lo = (uint32_t) __cvta_generic_to_shared(sm);
   const TileDims td = tile_dims(g.ng);
-  const uint32_t nwork = (uint32_t) NFIELD * (uint32_t) (td.ntx * td.nty * td.ntz);
+  const uint32_t ntile = (uint32_t) (td.ntx * td.nty * td.ntz);
   // |w wscale wx wy wz| <= wmax |wscale| for every scheme (PCS: weights in units of 1/6,
   // times 1/216)
   const double wbound = *wmax_dev * fabs(wscale);
-  for (int i = threadIdx.x; i < 2 * TCELLS; i += ACC_THREADS) sm[i] = 0;
+  for (int i = threadIdx.x; i < TCELLS / 2; i += ACC_THREADS) reinterpret_cast<uint4 *>(sm)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (threadIdx.x == 0) nqueue = 0;
   __syncthreads();
-  for (uint32_t work = blockIdx.x; work < nwork; work += gridDim.x) {
-    const uint32_t tile = work / NFIELD;
-    const int f = (int) (work % NFIELD);
+  for (uint32_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
     const int tz = tile % td.ntz, ty = (tile / td.ntz) % td.nty, tx = tile / (td.ntz * td.nty);
     const int x0 = tx * TX, y0 = ty * TY, z0 = tz * TZ;
     const uint32_t b0 = start[tile], np = start[tile + 1] - b0;
     // headroom: a cell receives at most one contribution per listed particle; the high
-    // limb holds 2^31 / 2^(S - LOBITS) contributions of the largest size
-    int S = 44;
-    for (uint32_t q = 1u << (31 - (44 - LOBITS)); q < np && S > 24; q <<= 1) S--;
+    // limb stays below 2^30 for 2^30 / 2^(S - LOBITS) contributions of the largest size
+    int S = 43;
+    for (uint32_t q = 1u << (30 - (43 - LOBITS)); q != 0u && q <= np; q <<= 1) S--;
     const double norm = wbound > 0.0 ? ldexp(1.0, S) / wbound : 0.0;
-    for (uint32_t base = 0; base < np; base += BATCH) {
-      const uint32_t lim = min(np, base + BATCH);
-      for (uint32_t j = base + threadIdx.x; j < lim; j += ACC_THREADS)
-        if (tile_add<SCHEME, false>(parts, (size_t) b0 + j, f, g, wscale, norm, x0, y0, z0, sm_lo))
-          queue[atomicAdd(&nqueue, 1u)] = j;
-      __syncthreads();
-      const uint32_t nq = nqueue;
-      for (uint32_t k = threadIdx.x; k < nq; k += ACC_THREADS)
-        tile_add<SCHEME, true>(parts, (size_t) b0 + queue[k], f, g, wscale, norm, x0, y0, z0, sm_lo);
-      __syncthreads();
-      if (threadIdx.x == 0) nqueue = 0;
-      if (lim < np) {
-        // fold the carries so that neither limb can wrap in the next batch
-        for (int i = threadIdx.x; i < TCELLS; i += ACC_THREADS) {
-          const uint32_t lo = sm[i];
-          sm[i] = lo & LOMASK;
-          sm[TCELLS + i] += lo >> LOBITS;
+    const double inv = wbound > 0.0 ? wbound * ldexp(1.0, -S) : 0.0;
+    const double wnorm = (SCHEME == 3 ? wscale * 0x1.2f684bda12f68p-8 : wscale) * norm;
+#pragma unroll 1
+    for (int f = 0; f < NFIELD; f++) {
+      for (uint32_t base = 0; base < np; base += BATCH) {
+        const uint32_t lim = min(np, base + BATCH);
+        for (uint32_t j = base + threadIdx.x; j < lim; j += ACC_THREADS)
+          if (tile_add<SCHEME, false>(parts, (size_t) b0 + j, f, g, wnorm, x0, y0, z0, sm_lo))
+            queue[atomicAdd(&nqueue, 1u)] = j;
+        __syncthreads();
+        const uint32_t nq = nqueue;
+        for (uint32_t k = threadIdx.x; k < nq; k += ACC_THREADS)
+          tile_add<SCHEME, true>(parts, (size_t) b0 + queue[k], f, g, wnorm, x0, y0, z0, sm_lo);
+        __syncthreads();
+        if (threadIdx.x == 0) nqueue = 0;
+        if (lim < np) {
+          // fold the carries so that neither limb can wrap in the next batch
+          for (int i = threadIdx.x; i < TCELLS; i += ACC_THREADS) {
+            const uint32_t lo = sm[2 * i];
+            sm[2 * i] = lo & LOMASK;
+            sm[2 * i + 1] += lo >> LOBITS;
+          }
+          __syncthreads();
+        }
+      }
+      // flush: every cell of the tile goes to the mesh once; the tile is left zeroed for
+      // the next work item
+      real *m = f ? mesh1 : mesh0;
+      if constexpr (TMA) {
+        for (int i = threadIdx.x; i < TCELLS / 2; i += ACC_THREADS) {
+          const uint4 q = reinterpret_cast<const uint4 *>(sm)[i];
+          reinterpret_cast<double2 *>(sm)[i] = make_double2(join_fixed(q.x, q.y) * inv, join_fixed(q.z, q.w) * inv);
+        }
+        // make the generic-proxy writes visible to the TMA engine, then one thread stores
+        // the box (z fastest); cells beyond the mesh are clipped by the tensor map
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];"
+              :: "l"(&maps.m[f]), "r"(z0), "r"(y0), "r"(x0), "r"(sm_lo) : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
         __syncthreads();
+        for (int i = threadIdx.x; i < TCELLS / 2; i += ACC_THREADS)
+          reinterpret_cast<uint4 *>(sm)[i] = make_uint4(0u, 0u, 0u, 0u);
       }
-    }
-    // flush: every cell of the tile goes to the mesh once, coalesced along z; the tile is
-    // left zeroed for the next work item
-    const double inv = wbound > 0.0 ? wbound * ldexp(1.0, -S) : 0.0;
-    real *m = f ? mesh1 : mesh0;
-    for (int c = threadIdx.x; c < TCELLS; c += ACC_THREADS) {
-      const int lzc = c % TZ, lyc = (c / TZ) % TY, lxc = c / (TZ * TY);
-      const uint32_t lo = sm[c], hi = sm[TCELLS + c];
-      sm[c] = 0u; sm[TCELLS + c] = 0u;
-      if (x0 + lxc < g.ng && y0 + lyc < g.ng && z0 + lzc < g.ng) {
-        const double v = ((double) (int) hi * (double) (1u << LOBITS) + (double) lo) * inv;
-        real *cell = m + ((size_t) (x0 + lxc) * g.ng + (y0 + lyc)) * g.rowlen + z0 + lzc;
-        if (MODE == 0) *cell = (real) v;
-        else *cell += (real) v;
+      else {
+        // two z-neighbours per thread: (row, pair) advance by ACC_THREADS pairs per step
+        constexpr int PAIRS = TZ / 2;
+        int row = threadIdx.x / PAIRS, q = threadIdx.x % PAIRS;
+        for (int i = threadIdx.x; i < TCELLS / 2; i += ACC_THREADS) {
+          const uint4 c = reinterpret_cast<const uint4 *>(sm)[i];
+          reinterpret_cast<uint4 *>(sm)[i] = make_uint4(0u, 0u, 0u, 0u);
+          const int gx = x0 + (row / TY), gy = y0 + (row % TY), gz = z0 + 2 * q;
+          if (gx < g.ng && gy < g.ng && gz < g.ng) {
+            const double v0 = join_fixed(c.x, c.y) * inv, v1 = join_fixed(c.z, c.w) * inv;
+            real *cell = m + ((size_t) gx * g.ng + gy) * g.rowlen + gz;
+            if (gz + 1 < g.ng) {
+              // rowlen and gz are even: the pair is aligned
+              if constexpr (sizeof(real) == 8) {
+                double2 *c2 = reinterpret_cast<double2 *>(cell);
+                if (MODE == 0) *c2 = make_double2(v0, v1);
+                else { double2 o = *c2; o.x += v0; o.y += v1; *c2 = o; }
+              }
+              else {
+                float2 *c2 = reinterpret_cast<float2 *>(cell);
+                if (MODE == 0) *c2 = make_float2((float) v0, (float) v1);
+                else { float2 o = *c2; o.x += (float) v0; o.y += (float) v1; *c2 = o; }
+              }
+            }
+            else {
+              if (MODE == 0) *cell = (real) v0;
+              else *cell += (real) v0;
+            }
+          }
+          q += ACC_THREADS % PAIRS;
+          row += ACC_THREADS / PAIRS;
+          if (q >= PAIRS) { q -= PAIRS; row++; }
+        }
       }
+      __syncthreads();
     }
-    __syncthreads();
   }
 }
+
+int g_fill_unroll = 4;  // particles in flight per thread of the fill pass (psb_set_option "tile_fill_unroll")
 
 template <int SCHEME, bool INTERLACE>
 int launch_lists(const double *p, size_t n, const AssignGeom &g, bool fill, uint32_t *cnt, double *out,
     double *partials, double *wmax_part, cudaStream_t st) {
   const double2 *pp = reinterpret_cast<const double2 *>(p);
   const int nblk = row_keys_blocks(n);
-  if (fill)
-    k_tile_lists<SCHEME, INTERLACE, true><<<nblk, 256, 0, st>>>(pp, n, g, cnt,
-        reinterpret_cast<double2 *>(out), nullptr, nullptr);
+  if (fill) {
+    double2 *o = reinterpret_cast<double2 *>(out);
+    if (g_fill_unroll >= 4) k_tile_lists<SCHEME, INTERLACE, true, 4><<<nblk, 256, 0, st>>>(pp, n, g, cnt, o, nullptr, nullptr);
+    else if (g_fill_unroll >= 2) k_tile_lists<SCHEME, INTERLACE, true, 2><<<nblk, 256, 0, st>>>(pp, n, g, cnt, o, nullptr, nullptr);
+    else k_tile_lists<SCHEME, INTERLACE, true, 1><<<nblk, 256, 0, st>>>(pp, n, g, cnt, o, nullptr, nullptr);
+  }
   else
-    k_tile_lists<SCHEME, INTERLACE, false><<<nblk, 256, 0, st>>>(pp, n, g, cnt, nullptr, partials, wmax_part);
+    k_tile_lists<SCHEME, INTERLACE, false, 2><<<nblk, 256, 0, st>>>(pp, n, g, cnt, nullptr, partials, wmax_part);
   PSB_CUDA(cudaGetLastError());
   return 0;
 }
 
+// cuTensorMapEncodeTiled through the runtime (the library does not link libcuda)
+typedef CUresult (*EncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiled tensor_map_encoder() {
+  static EncodeTiled fn = []() -> EncodeTiled {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiled>(p);
+  }();
+  return fn;
+}
+
+// the mesh as a (x, y, z) tensor of doubles whose z extent is the Ng cells of a row (not
+// its padding), box = one tile
+bool tile_tensor_map(CUtensorMap *tm, void *mesh, const AssignGeom &g) {
+  EncodeTiled enc = tensor_map_encoder();
+  if (!enc || !mesh || (reinterpret_cast<uintptr_t>(mesh) & 15)) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t) g.ng, (cuuint64_t) g.ng, (cuuint64_t) g.ng};
+  const cuuint64_t strides[2] = {(cuuint64_t) g.rowlen * 8, (cuuint64_t) g.ng * g.rowlen * 8};
+  const cuuint32_t box[3] = {TZ, TY, TX}, estr[3] = {1, 1, 1};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, mesh, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int g_tile_tma = 1;     // ablation switch (psb_set_option "tile_tma")
+
 template <int SCHEME, typename real>
 int launch_accumulate(const double *parts, const uint32_t *start, const AssignGeom &g, double wscale,
     const double *wmax, bool add, void *m0, void *m1, cudaStream_t st) {
-  const size_t smem = (size_t) 2 * TCELLS * 4;
+  const size_t smem = (size_t) TCELLS * 8;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const double2 *pp = reinterpret_cast<const double2 *>(parts);
   real *a = static_cast<real *>(m0), *b = static_cast<real *>(m1);
-#define PSB_ACC(NF, MODE)                                                                         \
+  TileMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  bool tma = false;
+  if constexpr (sizeof(real) == 8)
+    tma = g_tile_tma && !add && tile_tensor_map(&maps.m[0], m0, g) && (!m1 || tile_tensor_map(&maps.m[1], m1, g));
+#define PSB_ACC(NF, MODE, TMA)                                                                     \
   do {                                                                                            \
-    auto kern = k_tile_accumulate<SCHEME, real, NF, MODE>;                                        \
+    auto kern = k_tile_accumulate<SCHEME, real, NF, MODE, TMA>;                                   \
     PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
-    kern<<<2 * sms, ACC_THREADS, smem, st>>>(pp, start, g, wscale, wmax, a, b);                    \
+    kern<<<2 * sms, ACC_THREADS, smem, st>>>(pp, start, g, wscale, wmax, a, b, maps);              \
   } while (0)
-  if (m1) { if (add) PSB_ACC(2, 1); else PSB_ACC(2, 0); }
-  else { if (add) PSB_ACC(1, 1); else PSB_ACC(1, 0); }
+  if constexpr (sizeof(real) == 8) {
+    if (tma) { if (m1) PSB_ACC(2, 0, true); else PSB_ACC(1, 0, true); }
+  }
+  if (!tma) {
+    if (m1) { if (add) PSB_ACC(2, 1, false); else PSB_ACC(2, 0, false); }
+    else { if (add) PSB_ACC(1, 1, false); else PSB_ACC(1, 0, false); }
+  }
 #undef PSB_ACC
   PSB_CUDA(cudaGetLastError());
   return 0;
 }
 
 }  // namespace
+
+void tile_set_tma(int on) { g_tile_tma = on; }
+void tile_set_fill_unroll(int u) { g_fill_unroll = u; }
 
 // the whole mesh on this device, and tiles that a stencil range (<= 6 cells) can straddle
 // in at most two pieces

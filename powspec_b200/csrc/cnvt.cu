@@ -22,6 +22,7 @@
 
 #include "psb_internal.h"
 
+#include <algorithm>
 #include <cfloat>
 #include <climits>
 #include <cmath>
@@ -119,20 +120,22 @@ __global__ void __launch_bounds__(256) k_cnvt_interp(double2 *__restrict__ p, si
     const double zv = b.x;
     double dist = HUGE_VAL;
     if (!(zv < z[0] || zv >= z[nsp - 1])) {
-      size_t l = 0, u = nsp - 1, i = 0;
-      while (l <= u) {
-        i = (l + u) >> 1;
-        if (z[i + 1] <= zv) l = i + 1;
-        else if (z[i] > zv) u = i - 1;
-        else break;
+      // the interval z[i] <= zv < z[i + 1] (samples ascending, src/cnvt_coord.c:102-137)
+      size_t i = 0, above = nsp - 1;
+      while (above - i > 1) {
+        const size_t mid = i + ((above - i) >> 1);
+        if (z[mid] <= zv) i = mid;
+        else above = mid;
       }
-      const size_t j = i + 1;
-      const double ba = __dsub_rn(z[j], z[i]), xa = __dsub_rn(zv, z[i]), bx = __dsub_rn(z[j], zv);
-      const double ba2 = __dmul_rn(ba, ba);
-      const double lower = __dadd_rn(__dmul_rn(xa, d[j]), __dmul_rn(bx, d[i]));
-      const double cc = __dmul_rn(__dmul_rn(__dsub_rn(__dmul_rn(xa, xa), ba2), xa), ypp[j]);
-      const double dd = __dmul_rn(__dmul_rn(__dsub_rn(__dmul_rn(bx, bx), ba2), bx), ypp[i]);
-      dist = __ddiv_rn(__dadd_rn(lower, __dmul_rn(0x1.5555555555555p-3, __dadd_rn(cc, dd))), ba);
+      // cubic through the bracketing samples (z_lo, z_hi): linear part plus the two
+      // second-derivative terms, operations in the order of math/cspline.c:94-108
+      const double z_lo = z[i], z_hi = z[i + 1];
+      const double width = __dsub_rn(z_hi, z_lo), up = __dsub_rn(zv, z_lo), down = __dsub_rn(z_hi, zv);
+      const double width2 = __dmul_rn(width, width);
+      const double chord = __dadd_rn(__dmul_rn(up, d[i + 1]), __dmul_rn(down, d[i]));
+      const double bend_hi = __dmul_rn(__dmul_rn(__dsub_rn(__dmul_rn(up, up), width2), up), ypp[i + 1]);
+      const double bend_lo = __dmul_rn(__dmul_rn(__dsub_rn(__dmul_rn(down, down), width2), down), ypp[i]);
+      dist = __ddiv_rn(__dadd_rn(chord, __dmul_rn(0x1.5555555555555p-3, __dadd_rn(bend_hi, bend_lo))), width);
     }
     to_cartesian(a, b, dist);
     p[2 * q] = a;
@@ -183,55 +186,56 @@ void legauss_rule(int order, double *x, double *w) {
   }
 }
 
-// smallest order that converges on `num` redshifts spanning [zmin, zmax],
-// src/cnvt_coord.c:356-396 with the samples of :277-278; INT_MAX if none does
+// Smallest Legendre-Gauss order whose integral agrees with the previous order's to the
+// relative tolerance `err` on every one of `num` equally spaced redshifts of
+// [zmin, zmax] (the convergence test of src/cnvt_coord.c:356-396 on the samples of
+// :277-278; the comparison starts from 0 below the lowest order); INT_MAX if even the
+// highest order does not converge somewhere.
 int legauss_order(double om, double ol, double ok, double widx, double err, double zmin,
     double zmax, int num) {
-  std::vector<double> x((LG_MAX + 1) * (LG_MAX / 2 + 1)), w(x.size());
-  for (int n = LG_MIN; n <= LG_MAX; n++) legauss_rule(n, &x[n * (LG_MAX / 2 + 1)], &w[n * (LG_MAX / 2 + 1)]);
+  constexpr int SLOT = LG_MAX / 2 + 1;
+  std::vector<double> nodes((LG_MAX + 1) * SLOT), weights(nodes.size());
+  for (int n = LG_MIN; n <= LG_MAX; n++) legauss_rule(n, &nodes[n * SLOT], &weights[n * SLOT]);
   int order = 0;
   for (int i = 0; i < num; i++) {
     const double z = zmin + i * (zmax - zmin) / (num - 1);
-    double oint, nint = 0;
-    int n = LG_MIN - 1;
-    do {
-      if (n >= LG_MAX) { n = INT_MAX; break; }
-      oint = nint;
-      ++n;
-      nint = legauss(&x[n * (LG_MAX / 2 + 1)], &w[n * (LG_MAX / 2 + 1)], n, om, ol, ok, widx, z);
+    int need = INT_MAX;
+    double prev = 0;
+    for (int n = LG_MIN; n <= LG_MAX; n++) {
+      const double cur = legauss(&nodes[n * SLOT], &weights[n * SLOT], n, om, ol, ok, widx, z);
+      if (!(fabs(cur - prev) > cur * err)) { need = n; break; }
+      prev = cur;
     }
-    while (fabs(nint - oint) > nint * err);
-    if (order < n) order = n;
+    order = std::max(order, need);
   }
   return order;
 }
 
-// second derivatives of the natural cubic spline, math/cspline.c:38-82
-// (forward elimination / back substitution of the tridiagonal system)
-int cspline_second(const double *x, const double *y, size_t n, double *ypp) {
+// Second derivatives m[] of the natural cubic spline through (x, y): the tridiagonal
+// system  h[i-1] m[i-1] + 2 (h[i-1] + h[i]) m[i] + h[i] m[i+1] = 6 (s[i] - s[i-1])  with
+// m[0] = m[n-1] = 0, solved by the Thomas algorithm.  The individual operations are the
+// ones math/cspline.c:38-82 performs (interval widths and slopes first, pivot as a
+// reciprocal, right-hand side times 6), so the table — and with it every interpolated
+// distance — is the reference's to the last bit.
+int cspline_second(const double *x, const double *y, size_t n, double *m) {
   if (n < 2) return -1;
-  std::vector<double> cp(n);
-  double newx = x[1], newy = y[1];
-  double c = x[1] - x[0];
-  double newd = (y[1] - y[0]) / c;
-  cp[0] = cp[n - 1] = ypp[0] = ypp[n - 1] = 0;
-  size_t j = 1;
-  for (; j < n - 1; j++) {
-    const double oldx = newx, oldy = newy, a = c, oldd = newd;
-    newx = x[j + 1];
-    newy = y[j + 1];
-    c = newx - oldx;
-    newd = (newy - oldy) / c;
-    const double b = (c + a) * 2;
-    const double invd = 1 / (b - a * cp[j - 1]);
-    const double d = (newd - oldd) * 6;
-    ypp[j] = (d - a * ypp[j - 1]) * invd;
-    cp[j] = c * invd;
+  const size_t nseg = n - 1;
+  std::vector<double> h(nseg), slope(nseg), upper(n, 0.0);
+  for (size_t i = 0; i < nseg; i++) {
+    h[i] = x[i + 1] - x[i];
+    slope[i] = (y[i + 1] - y[i]) / h[i];
   }
-  while (j) {
-    j -= 1;
-    ypp[j] -= cp[j] * ypp[j + 1];
+  m[0] = m[n - 1] = 0;
+  // forward sweep over the interior nodes: upper[] is the eliminated super-diagonal
+  for (size_t i = 1; i < nseg; i++) {
+    const double diag = (h[i] + h[i - 1]) * 2;
+    const double pivot = 1 / (diag - h[i - 1] * upper[i - 1]);
+    const double rhs = (slope[i] - slope[i - 1]) * 6;
+    m[i] = (rhs - h[i - 1] * m[i - 1]) * pivot;
+    upper[i] = h[i] * pivot;
   }
+  // back substitution (upper[0] = 0: m[0] stays 0)
+  for (size_t i = nseg; i-- > 0;) m[i] -= upper[i] * m[i + 1];
   return 0;
 }
 

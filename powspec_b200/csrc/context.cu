@@ -1126,6 +1126,8 @@ int psb_set_option(psb_context *c, const char *name, long value) {
   if (!strcmp(name, "fft_own_x")) { c->opt_fft_own_x = value; return 0; }
   if (!strcmp(name, "fft_fused")) { c->opt_fft_fused = value; return 0; }
   if (!strcmp(name, "fft_variant")) { fft_set_variant((int) value); return 0; }
+  if (!strcmp(name, "tile_fill_unroll")) { tile_set_fill_unroll((int) value); return 0; }
+  if (!strcmp(name, "tile_tma")) { tile_set_tma((int) value); return 0; }
   if (!strcmp(name, "l2_fetch")) {          // L2 fetch granularity hint in bytes (32 / 64 / 128)
     if (cudaSetDevice(c->device) != cudaSuccess ||
         cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t) value) != cudaSuccess) {

@@ -61,6 +61,8 @@ int launch_assign(const double *p, size_t n, const AssignGeom &g, int scheme,
 // owner-computes assignment (assign_tiles.cu): per-tile particle lists, fixed-point
 // accumulation in shared memory, one plain store per mesh cell
 bool tile_assign_supported(const AssignGeom &g);
+void tile_set_fill_unroll(int u);
+void tile_set_tma(int on);      // 0: flush tiles with thread stores instead of TMA tensor stores (ablation)
 size_t tile_list_count(const AssignGeom &g);
 int launch_tile_count(const double *p, size_t n, const AssignGeom &g, int scheme, bool interlace,
     uint32_t *cnt, double *partials, double *wmax_part, double *wmax, cudaStream_t st);
