@@ -2,7 +2,7 @@
 """Per-source-line instruction and stall-sample totals of one kernel of an ncu report
 (captured with --import-source on, code built with -lineinfo).  Run here, no GPU needed.
 
-    python tools/ncu_lines.py gpurun_out/x.ncu-rep kernel_regex [top_n]
+    python tools/ncu_lines.py gpurun_out/x.ncu-rep kernel_regex [top_n] [samples]
 """
 import csv
 import io
@@ -14,6 +14,7 @@ from collections import defaultdict
 def main():
     rep, pat = sys.argv[1], sys.argv[2]
     top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+    by = 1 if (len(sys.argv) > 4 and sys.argv[4] == "samples") else 0
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass",
                           "--kernel-name", "regex:" + pat], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
@@ -47,7 +48,7 @@ def main():
     tot_i = sum(v[0] for v in per.values()) or 1
     tot_s = sum(v[1] for v in per.values()) or 1
     print(f"total warp instructions {tot_i:.4g}, samples {tot_s:.0f}")
-    for k, v in sorted(per.items(), key=lambda kv: -kv[1][0])[:top]:
+    for k, v in sorted(per.items(), key=lambda kv: -kv[1][by])[:top]:
         print(f"{100 * v[0] / tot_i:5.1f}% inst {100 * v[1] / tot_s:5.1f}% smp  {k[0]:>24} {k[1]}")
 
 
