@@ -91,7 +91,8 @@ _lib = None
 
 
 def library_path() -> str:
-    return os.path.join(HERE, "libpowspec_b200.so")
+    # POWSPEC_B200_LIBRARY: an ablation build of the same library (tools/build_variant.sh)
+    return os.environ.get("POWSPEC_B200_LIBRARY") or os.path.join(HERE, "libpowspec_b200.so")
 
 
 def load_library():
@@ -529,11 +530,21 @@ class Context:
             raise _err(self.L, "cnvt_coord", POWSPEC_ERR_CNVT)
         return order.value
 
+    @staticmethod
+    def _after_torch():
+        """The library works on its own (non-blocking) stream: a tensor that torch has just
+        produced on ITS stream must be complete before the library touches it (found by
+        running the FFT tests under compute-sanitizer, whose slowdown exposed the missing
+        ordering in the test helpers)."""
+        import torch
+        torch.cuda.current_stream().synchronize()
+
     def fft_axis(self, tensor, axis: int):
         """In-place forward FFT along axis 0 or 1 of a 3-D complex CUDA tensor
         (hand-written strided pass; the other two axes are (outer, k))."""
         prec = 8 if tensor.element_size() == 16 else 4
         ng = tensor.shape[axis]
+        self._after_torch()
         if self.L.psb_fft_axis(self.h, tensor.data_ptr(), prec, ng, tensor.shape[2], axis,
                                tensor.shape[1 - axis]):
             raise _err(self.L, "psb_fft_axis")
@@ -544,6 +555,7 @@ class Context:
         (hand-written z pass); returns the complex (nrows, ng/2+1) view."""
         import torch
         prec = tensor.element_size()
+        self._after_torch()
         if self.L.psb_fft_axis(self.h, tensor.data_ptr(), prec, ng, ng // 2 + 1, 2, tensor.shape[0]):
             raise _err(self.L, "psb_fft_axis")
         return torch.view_as_complex(tensor.view(tensor.shape[0], ng // 2 + 1, 2))
@@ -553,6 +565,7 @@ class Context:
         tensor (fused persistent kernel); returns the complex (nplanes, ng, ng/2+1) view."""
         import torch
         npl, ng, rl = tensor.shape
+        self._after_torch()
         if self.L.psb_fft_axis(self.h, tensor.data_ptr(), tensor.element_size(), ng, rl // 2, 3, npl):
             raise _err(self.L, "psb_fft_axis")
         return torch.view_as_complex(tensor.view(npl, ng, rl // 2, 2))

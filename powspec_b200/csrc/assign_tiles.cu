@@ -44,12 +44,22 @@ namespace psb {
 
 namespace {
 
-constexpr int TX = 16, TY = 16, TZ = 48;
+// tile shape / block shape of the accumulation (macros: ablation builds, profiles/README.md)
+#ifndef PSB_TILE_TZ
+#define PSB_TILE_TZ 48
+#endif
+#ifndef PSB_ACC_THREADS
+#define PSB_ACC_THREADS 512
+#endif
+#ifndef PSB_ACC_BLOCKS
+#define PSB_ACC_BLOCKS 2
+#endif
+constexpr int TX = 16, TY = 16, TZ = PSB_TILE_TZ;
 constexpr int TCELLS = TX * TY * TZ;
 constexpr int LOBITS = 21;
 constexpr unsigned LOMASK = (1u << LOBITS) - 1;
 constexpr unsigned BATCH = 1u << (32 - LOBITS);
-constexpr int ACC_THREADS = 512;
+constexpr int ACC_THREADS = PSB_ACC_THREADS, ACC_BLOCKS = PSB_ACC_BLOCKS;
 
 struct TileDims { int ntx, nty, ntz; };
 
@@ -343,11 +353,11 @@ struct TileMaps { CUtensorMap m[2]; };
 // MODE 0: the tile is stored (the mesh need not be initialised); 1: added to the mesh.
 // TMA: the flush of a double-precision tile is one bulk tensor store.
 template <int SCHEME, typename real, int NFIELD, int MODE, bool TMA>
-__global__ void __launch_bounds__(ACC_THREADS, 2) k_tile_accumulate(const double2 *__restrict__ parts,
+__global__ void __launch_bounds__(ACC_THREADS, ACC_BLOCKS) k_tile_accumulate(const double2 *__restrict__ parts,
     const uint32_t *__restrict__ start, AssignGeom g, double wscale, const double *__restrict__ wmax_dev,
     real *__restrict__ mesh0, real *__restrict__ mesh1, const __grid_constant__ TileMaps maps) {
   extern __shared__ __align__(1024) uint32_t sm[];      // cell c: words 2c, 2c + 1 = its limbs (limb_swap)
-  __shared__ uint32_t queue[BATCH];             // listed particles that straddle the tile's z faces
+  __shared__ uint16_t queue[BATCH];             // listed particles (index in the batch) that straddle the tile's z faces
   __shared__ uint32_t nqueue;
   const uint32_t sm_lo = (uint32_t) __cvta_generic_to_shared(sm);
   const TileDims td = tile_dims(g.ng);
@@ -375,11 +385,11 @@ __global__ void __launch_bounds__(ACC_THREADS, 2) k_tile_accumulate(const double
         const uint32_t lim = min(np, base + BATCH);
         for (uint32_t j = base + threadIdx.x; j < lim; j += ACC_THREADS)
           if (tile_add<SCHEME, false>(parts, (size_t) b0 + j, f, g, wnorm, x0, y0, z0, sm_lo))
-            queue[atomicAdd(&nqueue, 1u)] = j;
+            queue[atomicAdd(&nqueue, 1u)] = (uint16_t) (j - base);
         __syncthreads();
         const uint32_t nq = nqueue;
         for (uint32_t k = threadIdx.x; k < nq; k += ACC_THREADS)
-          tile_add<SCHEME, true>(parts, (size_t) b0 + queue[k], f, g, wnorm, x0, y0, z0, sm_lo);
+          tile_add<SCHEME, true>(parts, (size_t) b0 + base + queue[k], f, g, wnorm, x0, y0, z0, sm_lo);
         __syncthreads();
         if (threadIdx.x == 0) nqueue = 0;
         if (lim < np) {
@@ -526,7 +536,7 @@ int launch_accumulate(const double *parts, const uint32_t *start, const AssignGe
   do {                                                                                            \
     auto kern = k_tile_accumulate<SCHEME, real, NF, MODE, TMA>;                                   \
     PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
-    kern<<<2 * sms, ACC_THREADS, smem, st>>>(pp, start, g, wscale, wmax, a, b, maps);              \
+    kern<<<ACC_BLOCKS * sms, ACC_THREADS, smem, st>>>(pp, start, g, wscale, wmax, a, b, maps);              \
   } while (0)
   if constexpr (sizeof(real) == 8) {
     if (tma) { if (m1) PSB_ACC(2, 0, true); else PSB_ACC(1, 0, true); }
