@@ -103,7 +103,10 @@ __device__ __forceinline__ double2 ld_c(const void *base, size_t idx) {
 // MODE_GEOM : v = {cnt, km, lcnt[0..nl)}            NV = nl + 2
 // MODE_SIM  : v = {pl[0..nl)}                       NV = nl
 // MODE_SURVEY: v = {pl}                             NV = 1
-template <typename real, int NV, int MODE, bool INTERLACE>
+// EVEN: the multipoles are 0, 2, 4, ... (poles[l] = 2 l, the usual request): ell is a
+// compile-time constant of the unrolled loop, so the Legendre switch and the odd-ell test
+// fold away (7 % of the instructions of this issue-bound kernel)
+template <typename real, int NV, int MODE, bool INTERLACE, bool EVEN = false>
 __global__ void __launch_bounds__(256) k_spectrum(BinGeom g, const void *__restrict__ Fa0,
     const void *__restrict__ Fa1, const void *__restrict__ Fb0,
     const void *__restrict__ Fb1, double *__restrict__ partials) {
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(256) k_spectrum(BinGeom g, const void *__restr
             }
 #pragma unroll
             for (int l = 0; l < NV - L0; l++) {
-              const int ell = g.poles[l];
+              const int ell = EVEN ? 2 * l : g.poles[l];
               // +mu / -mu half-planes cancel for odd ell (src/multipole.c:843-844):
               // only the k = 0 and Nyquist planes contribute (quirk Q6)
               if (!edge && (ell & 1)) continue;
@@ -308,10 +311,10 @@ int shape_for(K kernel, int nacc, int nbin, LaunchShape &ls) {
 
 constexpr int MAX_BLOCKS = 148 * 8;
 
-template <typename real, int NV, int MODE, bool IL>
+template <typename real, int NV, int MODE, bool IL, bool EVEN = false>
 int run_spectrum(const BinGeom &g, const void *Fa0, const void *Fa1, const void *Fb0,
     const void *Fb1, double *out, double *scratch, size_t scratch_bytes, cudaStream_t st) {
-  auto kern = k_spectrum<real, NV, MODE, IL>;
+  auto kern = k_spectrum<real, NV, MODE, IL, EVEN>;
   const int nacc = NV * g.nbin;
   LaunchShape ls;
   if (shape_for(kern, nacc, g.nbin, ls)) return -1;
@@ -375,6 +378,15 @@ static int launch_bin_t(const BinGeom &g, const void *Fa0, const void *Fa1, cons
     return il ? run_spectrum<real, 1, MODE_SURVEY, true>(g, Fa0, Fa1, Fb0, Fb1, pl, scratch, sb, st)
               : run_spectrum<real, 1, MODE_SURVEY, false>(g, Fa0, Fa1, Fb0, Fb1, pl, scratch, sb, st);
   }
+  bool even = g.nl <= 4;
+  for (int l = 0; l < g.nl; l++) even = even && g.poles[l] == 2 * l;
+#define PSB_SIM_EVEN(NL)                                                        \
+  case NL:                                                                      \
+    return il ? run_spectrum<real, NL, MODE_SIM, true, true>(g, Fa0, Fa1, Fb0, Fb1, pl, scratch, sb, st)  \
+              : run_spectrum<real, NL, MODE_SIM, false, true>(g, Fa0, Fa1, Fb0, Fb1, pl, scratch, sb, st);
+  if (even)
+    switch (g.nl) { PSB_SIM_EVEN(1) PSB_SIM_EVEN(2) PSB_SIM_EVEN(3) PSB_SIM_EVEN(4) default: break; }
+#undef PSB_SIM_EVEN
 #define PSB_SIM(NL)                                                             \
   case NL:                                                                      \
     return il ? run_spectrum<real, NL, MODE_SIM, true>(g, Fa0, Fa1, Fb0, Fb1, pl, scratch, sb, st)  \
