@@ -2,8 +2,8 @@
 // formulation of the assignment loops of src/genr_mesh.c:50-412, 793-858):
 //
 //   1. k_tile_lists<count> / scan / k_tile_lists<fill>: every particle is appended to the
-//      list of every mesh TILE (16 x 16 x 48 cells) that the stencils of its fields reach
-//      — 1.41 entries per particle for TSC + interlacing;
+//      list of every mesh TILE (16 x 16 x 32 cells) that the stencils of its fields reach
+//      — 1.46 entries per particle for TSC + interlacing;
 //   2. k_tile_accumulate: one block per (tile, field) keeps the tile in shared memory as
 //      FIXED-POINT numbers in two 32-bit limbs and adds the in-tile part of each listed
 //      particle's stencil with the native shared-memory ATOMS.ADD — the only shared atomic
@@ -46,13 +46,13 @@ namespace {
 
 // tile shape / block shape of the accumulation (macros: ablation builds, profiles/README.md)
 #ifndef PSB_TILE_TZ
-#define PSB_TILE_TZ 48
+#define PSB_TILE_TZ 32
 #endif
 #ifndef PSB_ACC_THREADS
-#define PSB_ACC_THREADS 512
+#define PSB_ACC_THREADS 384
 #endif
 #ifndef PSB_ACC_BLOCKS
-#define PSB_ACC_BLOCKS 2
+#define PSB_ACC_BLOCKS 3
 #endif
 constexpr int TX = 16, TY = 16, TZ = PSB_TILE_TZ;
 constexpr int TCELLS = TX * TY * TZ;

@@ -749,6 +749,16 @@ int fft_forward(psb_context *c, void *mesh, bool skip_ok) {
     // (3.5 vs 4.1 ms at 1024^3); ours wins in single precision and for 1536 = 2^9 3
     // (cuFFT: 38 ms per 1536^3 pass)
     const bool own_z = fft_own_z(c, ng, prec);
+    // cells beyond the last bin edge are never read when only the binning follows: the x
+    // pass skips their tiles, and neither pass stores them (FftStoreSkip)
+    const bool skip = skip_ok && c->opt_fft_skip && c->bins_ready;
+    const bool sskip = skip && c->opt_fft_store_skip && fft_own_x(c, ng, prec);
+    FftStoreSkip ss_y, ss_x;
+    if (sskip) {
+      ss_y.k2t = c->bg.kax2[1]; ss_y.k2k = c->bg.kax2[2]; ss_y.k2max = c->fft_k2max;
+      ss_x.k2t = c->bg.kax2[0]; ss_x.k2o = c->bg.kax2[1]; ss_x.k2k = c->bg.kax2[2];
+      ss_x.k2max = c->fft_k2max; ss_x.per_column = 1;
+    }
     if (c->opt_fft_fused && zp == ng) {
       // z + y in one persistent kernel, handed over plane by plane through the L2
       if (c->fftdone.reserve(sizeof(int) * (size_t) ng)) return -1;
@@ -775,7 +785,7 @@ int fft_forward(psb_context *c, void *mesh, bool skip_ok) {
           if (prec == 8) PSB_CUFFT(cufftExecD2Z(pz, (cufftDoubleReal *) grp, (cufftDoubleComplex *) grp));
           else PSB_CUFFT(cufftExecR2C(pz, (cufftReal *) grp, (cufftComplex *) grp));
         }
-        if (launch_fft_strided(grp, prec, ng, ngk, 1, zp, nullptr, nullptr, 0.0, sg)) return -1;
+        if (launch_fft_strided(grp, prec, ng, ngk, 1, zp, nullptr, nullptr, 0.0, sg, sskip ? &ss_y : nullptr)) return -1;
         c->launches += 2;
       }
       if (two) {
@@ -792,9 +802,8 @@ int fft_forward(psb_context *c, void *mesh, bool skip_ok) {
         PSB_CUFFT(cufftExecC2C(c->plan_x, (cufftComplex *) mesh, (cufftComplex *) mesh, CUFFT_FORWARD));
       return 0;
     }
-    const bool skip = skip_ok && c->opt_fft_skip && c->bins_ready;
     if (launch_fft_strided(mesh, prec, ng, ngk, 0, ng, skip ? c->bg.kax2[1] : nullptr,
-          skip ? c->bg.kax2[2] : nullptr, c->fft_k2max, c->st))
+          skip ? c->bg.kax2[2] : nullptr, c->fft_k2max, c->st, sskip ? &ss_x : nullptr))
       return -1;
     return 0;
   }
@@ -1126,6 +1135,7 @@ int psb_set_option(psb_context *c, const char *name, long value) {
   if (!strcmp(name, "fft_own_x")) { c->opt_fft_own_x = value; return 0; }
   if (!strcmp(name, "fft_fused")) { c->opt_fft_fused = value; return 0; }
   if (!strcmp(name, "fft_variant")) { fft_set_variant((int) value); return 0; }
+  if (!strcmp(name, "fft_store_skip")) { c->opt_fft_store_skip = value; return 0; }
   if (!strcmp(name, "tile_fill_unroll")) { tile_set_fill_unroll((int) value); return 0; }
   if (!strcmp(name, "tile_tma")) { tile_set_tma((int) value); return 0; }
   if (!strcmp(name, "l2_fetch")) {          // L2 fetch granularity hint in bytes (32 / 64 / 128)

@@ -757,6 +757,7 @@ psb_result *psb_dist_finish(psb_dist *d, const double wdata[2]) {
   if (G > 1 && !p2p && nc * nf > 1 && d->xbuf2.reserve(sb)) return fail();
   const int nt = nc * nf;
   void *kspace[4] = {nullptr, nullptr, nullptr, nullptr};
+  double sent_frac = 1.0;
   cudaEvent_t ev_packed[4], ev_recv[4];
   for (int t = 0; t < nt; t++) { ev_packed[t] = get_event(c); ev_recv[t] = get_event(c); }
   auto release_events = [&]() { for (int t = 0; t < nt; t++) { c->evpool.push_back(ev_packed[t]); c->evpool.push_back(ev_recv[t]); } };
@@ -803,7 +804,27 @@ psb_result *psb_dist_finish(psb_dist *d, const double wdata[2]) {
         if (G == 1) {
           if (launch_fft_strided(owned, prec, ng, ngk, 1, nx, nullptr, nullptr, 0.0, st)) return fail();
         }
-        else if (launch_fft_strided_out(owned, prec, ng, ngk, nx, out, st)) return fail();
+        else {
+          // rows beyond the last bin edge are neither stored nor sent (the x pass on the
+          // receiving rank skips their tiles by the same test)
+          FftStoreSkip ss;
+          const bool sskip = c->opt_fft_skip && c->opt_fft_store_skip && c->slab_own_x && c->bins_ready;
+          if (sskip) {
+            if (hard(cudaStreamWaitEvent(st, c->ev_geom, 0))) return fail();
+            ss.k2t = c->bg.kax2[1]; ss.k2k = c->bg.kax2[2];
+            ss.k2max = c->host_tables[15 * (size_t) ng + c->nbin];
+          }
+          if (launch_fft_strided_out(owned, prec, ng, ngk, nx, out, st, sskip ? &ss : nullptr)) return fail();
+          if (sskip && t == 0) {
+            // fraction of the (y, k) rows that are stored (per column; the kernel decides per
+            // tile of columns, so slightly more is sent): what really crosses the links
+            const double *ky2 = &c->host_tables[(size_t) (3 + 1) * ng], *kz2 = &c->host_tables[(size_t) (3 + 2) * ng];
+            size_t kept = 0;
+            for (int y = 0; y < ng; y++)
+              for (int k = 0; k < ngk; k++) kept += (ky2[y] + kz2[k] < ss.k2max);
+            sent_frac = (double) kept / ((double) ng * ngk);
+          }
+        }
         c->launches += 2;
       }
       else {
@@ -823,7 +844,7 @@ psb_result *psb_dist_finish(psb_dist *d, const double wdata[2]) {
       }
     }
     if (G > 1) {
-      d->a2a_bytes += (double) blk * (G - 1);
+      d->a2a_bytes += (double) blk * (G - 1) * (p2p ? sent_frac : 1.0);
       if (p2p) {
         // the stores into the peers are complete when every rank's kernel is: a
         // stream-ordered barrier; it also releases this field's slab buffer as the
@@ -853,8 +874,14 @@ psb_result *psb_dist_finish(psb_dist *d, const double wdata[2]) {
       const bool skip = c->opt_fft_skip != 0;
       const double k2max = c->host_tables[15 * (size_t) ng + c->nbin];
       if (skip && hard(cudaStreamWaitEvent(st, c->ev_geom, 0))) { release_events(); return fail(); }
+      FftStoreSkip ss;
+      const bool sskip = skip && c->opt_fft_store_skip;
+      if (sskip) {
+        ss.k2t = c->bg.kax2[0]; ss.k2o = c->bg.kax2[1] + d->g.x0; ss.k2k = c->bg.kax2[2];
+        ss.k2max = k2max; ss.per_column = 1;
+      }
       if (launch_fft_strided(kspace[t], prec, ng, ngk, 0, nx, skip ? c->bg.kax2[1] + d->g.x0 : nullptr,
-            skip ? c->bg.kax2[2] : nullptr, k2max, st)) { release_events(); return fail(); }
+            skip ? c->bg.kax2[2] : nullptr, k2max, st, sskip ? &ss : nullptr)) { release_events(); return fail(); }
     }
     else if (prec == 8 ? cufftExecZ2Z(c->slab_x, (cufftDoubleComplex *) kspace[t], (cufftDoubleComplex *) kspace[t], CUFFT_FORWARD) != CUFFT_SUCCESS
                        : cufftExecC2C(c->slab_x, (cufftComplex *) kspace[t], (cufftComplex *) kspace[t], CUFFT_FORWARD) != CUFFT_SUCCESS) {

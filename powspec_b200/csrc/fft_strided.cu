@@ -257,7 +257,7 @@ template <typename T, int R3, int TK, int MINB>
 __global__ void __launch_bounds__(Shape<R3, TK>::THREADS, MINB)
 k_fft_strided(typename Mem<T>::gmem_t *__restrict__ data, int ngk, int outer_n, size_t outer_stride,
     size_t estride, const double *__restrict__ k2a, const double *__restrict__ k2b, double k2max,
-    FftOut out) {
+    FftOut out, FftStoreSkip ss) {
   using S = Shape<R3, TK>;
   using E = El<T>;
   using MM = Mem<T>;
@@ -335,6 +335,15 @@ k_fft_strided(typename Mem<T>::gmem_t *__restrict__ data, int ngk, int outer_n, 
 #pragma unroll
       for (int m = 0; m < 16; m++) a[m] = MM::load(ng_, (size_t) (u + M * m) * estride, TK, nla, nlb);
     }
+    // outputs beyond the last bin edge are not stored (FftStoreSkip): per tile, the part of
+    // the test that does not depend on the output index
+    double ska = 0.0, skb = 0.0, sko = 0.0;
+    if (ss.k2t) {
+      const int o = (int) (tile / ktiles), k0 = (int) (tile % ktiles) * WIDTH;
+      sko = ss.k2o ? __ldg(ss.k2o + o) : 0.0;
+      ska = __ldg(ss.k2k + (ss.per_column ? min(k0 + c, ngk - 1) : k0));
+      skb = __ldg(ss.k2k + (ss.per_column ? min(k0 + c + TK, ngk - 1) : k0));
+    }
     // ---- pass 3: radix R3 over t1 for the 256 (p, q1) pairs; X[p + 16 q1 + 256 q2]
     for (int pair = u; pair < 256; pair += M) {
       const int p3 = pair & 15, q1 = pair >> 4;
@@ -344,8 +353,16 @@ k_fft_strided(typename Mem<T>::gmem_t *__restrict__ data, int ngk, int outer_n, 
       SmallDft<T, R3>::run(d);
       if (out.ny == 0) {
 #pragma unroll
-        for (int q2 = 0; q2 < R3; q2++)
-          MM::store(g, (size_t) (p3 + 16 * q1 + 256 * q2) * estride, TK, la, lb, d[q2]);
+        for (int q2 = 0; q2 < R3; q2++) {
+          const int n = p3 + 16 * q1 + 256 * q2;
+          bool ka = la, kb = lb;
+          if (ss.k2t) {
+            const double kto = __ldg(ss.k2t + n) + sko;
+            ka = ka && (kto + ska < ss.k2max);
+            kb = kb && (kto + skb < ss.k2max);
+          }
+          MM::store(g, (size_t) n * estride, TK, ka, kb, d[q2]);
+        }
       }
       else {
         // transposed output for the slab decomposition: point y of the transform goes to
@@ -354,7 +371,13 @@ k_fft_strided(typename Mem<T>::gmem_t *__restrict__ data, int ngk, int outer_n, 
 #pragma unroll
         for (int q2 = 0; q2 < R3; q2++) {
           const int y = p3 + 16 * q1 + 256 * q2, blk = y / out.ny;
-          MM::store(static_cast<G *>(out.base[blk]) + oo, (size_t) (y - blk * out.ny) * ngk, TK, la, lb,
+          bool ka = la, kb = lb;
+          if (ss.k2t) {
+            const double kto = __ldg(ss.k2t + y) + sko;
+            ka = ka && (kto + ska < ss.k2max);
+            kb = kb && (kto + skb < ss.k2max);
+          }
+          MM::store(static_cast<G *>(out.base[blk]) + oo, (size_t) (y - blk * out.ny) * ngk, TK, ka, kb,
               d[q2]);
         }
       }
@@ -366,7 +389,7 @@ k_fft_strided(typename Mem<T>::gmem_t *__restrict__ data, int ngk, int outer_n, 
 
 template <typename T, int R3, int TK, int MINB>
 int launch_shape(void *data, int ng, int ngk, int axis, int outer_n, const double *k2a,
-    const double *k2b, double k2max, const FftOut &out, cudaStream_t st) {
+    const double *k2b, double k2max, const FftOut &out, const FftStoreSkip &ss, cudaStream_t st) {
   using S = Shape<R3, TK>;
   using G = typename Mem<T>::gmem_t;
   const size_t smem = (size_t) TK * S::PITCH * 16;
@@ -386,10 +409,10 @@ int launch_shape(void *data, int ng, int ngk, int axis, int outer_n, const doubl
   //         outer index = the row inside the plane.
   if (axis == 1)
     kern<<<grid, S::THREADS, smem, st>>>(static_cast<G *>(data), ngk, outer_n,
-        (size_t) ng * ngk, row, nullptr, nullptr, 0.0, out);
+        (size_t) ng * ngk, row, nullptr, nullptr, 0.0, out, ss);
   else
     kern<<<grid, S::THREADS, smem, st>>>(static_cast<G *>(data), ngk, outer_n, row,
-        (size_t) outer_n * ngk, k2a, k2b, k2max, FftOut{});
+        (size_t) outer_n * ngk, k2a, k2b, k2max, FftOut{}, ss);
   PSB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -821,14 +844,14 @@ int launch_rows_any(const void *src, void *dst, int ng, long nrows, size_t src_p
 
 template <typename T>
 int launch_any(void *data, int ng, int ngk, int axis, int outer_n, const double *k2a,
-    const double *k2b, double k2max, const FftOut &out, cudaStream_t st) {
+    const double *k2b, double k2max, const FftOut &out, const FftStoreSkip &ss, cudaStream_t st) {
   switch (ng) {
-    case 512: return launch_shape<T, 2, 16, 1>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, out, st);
+    case 512: return launch_shape<T, 2, 16, 1>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, out, ss, st);
     case 1024:
-      if (g_fft_variant == 1) return launch_shape<T, 4, 4, 2>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, out, st);
-      return launch_shape<T, 4, 8, 1>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, out, st);
-    case 1536: return launch_shape<T, 6, 4, 1>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, out, st);
-    case 2048: return launch_shape<T, 8, 4, 1>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, out, st);
+      if (g_fft_variant == 1) return launch_shape<T, 4, 4, 2>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, out, ss, st);
+      return launch_shape<T, 4, 8, 1>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, out, ss, st);
+    case 1536: return launch_shape<T, 6, 4, 1>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, out, ss, st);
+    case 2048: return launch_shape<T, 8, 4, 1>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, out, ss, st);
     default:
       set_error("no hand-written strided FFT for GRID_SIZE %d\n", ng);
       return -1;
@@ -848,10 +871,11 @@ bool fft_strided_supported(int ng, int precision) {
 // axis 1: along y of (outer_n, ng, ngk); axis 0: along x of (ng, outer_n, ngk)
 // (outer_n = ng on a single GPU, the y-slab height in the slab-decomposed path).
 int launch_fft_strided(void *data, int precision, int ng, int ngk, int axis, int outer_n,
-    const double *k2a, const double *k2b, double k2max, cudaStream_t st) {
+    const double *k2a, const double *k2b, double k2max, cudaStream_t st, const FftStoreSkip *ss) {
+  const FftStoreSkip none, &s = ss ? *ss : none;
   if (precision == 8)
-    return launch_any<double>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, FftOut{}, st);
-  return launch_any<float>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, FftOut{}, st);
+    return launch_any<double>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, FftOut{}, s, st);
+  return launch_any<float>(data, ng, ngk, axis, outer_n, k2a, k2b, k2max, FftOut{}, s, st);
 }
 
 // The y pass of the slab-decomposed transform with the transpose's packing (and, when
@@ -859,15 +883,16 @@ int launch_fft_strided(void *data, int precision, int ng, int ngk, int axis, int
 // (outer_n, ng, ngk) from `data`, writes point y of plane o to
 // out.base[y / out.ny] + (o * out.outer_stride + (y % out.ny) * ngk + k).
 int launch_fft_strided_out(const void *data, int precision, int ng, int ngk, int outer_n,
-    const FftOut &out, cudaStream_t st) {
+    const FftOut &out, cudaStream_t st, const FftStoreSkip *ss) {
+  const FftStoreSkip none, &s = ss ? *ss : none;
   if (out.ny <= 0 || ng % out.ny || ng / out.ny > FftOut::MAXB) {
     set_error("invalid transposed-output layout for the y pass\n");
     return -1;
   }
   void *d = const_cast<void *>(data);
   if (precision == 8)
-    return launch_any<double>(d, ng, ngk, 1, outer_n, nullptr, nullptr, 0.0, out, st);
-  return launch_any<float>(d, ng, ngk, 1, outer_n, nullptr, nullptr, 0.0, out, st);
+    return launch_any<double>(d, ng, ngk, 1, outer_n, nullptr, nullptr, 0.0, out, s, st);
+  return launch_any<float>(d, ng, ngk, 1, outer_n, nullptr, nullptr, 0.0, out, s, st);
 }
 
 // z and y passes of nplanes planes of a (nplanes, ng, 2 ngk) real mesh in place,

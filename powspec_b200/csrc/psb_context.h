@@ -121,6 +121,7 @@ struct psb_context {
   long opt_coop_variant = 0;
   long opt_survey_direct = 1;           // survey l > 0: bin Fk0 x Fka_m directly (no Fkl field)
   long opt_fft_skip = 1;                // x pass skips the columns beyond the last bin edge
+  long opt_fft_store_skip = 1;          // the y and x passes do not store cells beyond the last bin edge
   long opt_fft_l2_mb = 0;               // L2 budget of a z + y plane group (0: whole mesh at once)
   long opt_fft_streams = 1;             // 2: alternate the plane groups between two streams
   long opt_fft_fused = 0;               // z + y passes in one persistent kernel (L2 hand-over)

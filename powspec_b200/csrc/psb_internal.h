@@ -146,11 +146,23 @@ struct FftOut {
   int ny = 0;                   // 0: in place
   size_t outer_stride = 0;      // elements between outer indices inside a block (ny * ngk)
 };
+// Outputs that nobody reads need not be stored: the binning drops every cell whose
+// (k_x^2 + k_y^2) + k_z^2 is not below the last bin edge (src/multipole.c:151-159), and the
+// x pass skips whole tiles by the same test.  (k2t[n] + k2o[o]) + k2k[kk] < k2max keeps
+// output n of the transformed axis (o = outer index; kk = the column, or the first column
+// of the tile when per_column = 0 — the granularity of the x pass's tile test, for the y
+// pass that feeds it).  Same additions in the same order as binning.cu, so no cell the
+// binning uses is ever dropped.  k2t = nullptr: store everything.
+struct FftStoreSkip {
+  const double *k2t = nullptr, *k2o = nullptr, *k2k = nullptr;
+  double k2max = 0;
+  int per_column = 0;
+};
 int launch_fft_strided_out(const void *data, int precision, int ng, int ngk, int outer_n,
-    const FftOut &out, cudaStream_t st);
+    const FftOut &out, cudaStream_t st, const FftStoreSkip *ss = nullptr);
 void fft_set_variant(int v);
 int launch_fft_strided(void *data, int precision, int ng, int ngk, int axis, int outer_n,
-    const double *k2a, const double *k2b, double k2max, cudaStream_t st);
+    const double *k2a, const double *k2b, double k2max, cudaStream_t st, const FftStoreSkip *ss = nullptr);
 
 // z + y passes of a whole mesh in one persistent kernel (L2-resident hand-over)
 int launch_fft_zy(void *mesh, int precision, int ng, int ngk, int nplanes, int *done,
