@@ -1317,6 +1317,13 @@ int psb_mesh(psb_context *c, const psb_params *par, const psb_cats *cats) {
     }
   }
   trace_mark("psb_mesh: all uploads and scatters enqueued");
+  // The FFT plans belong to mesh generation in the reference too (mesh_init,
+  // src/genr_mesh.c:738-743).  Creating them HERE, while the device is still busy with the
+  // uploads and scatters queued above, takes the first call's ~60 ms of cuFFT
+  // initialisation off the critical path of a one-shot caller (the reference's C host
+  // calls genr_mesh / powspec once per process).
+  if (ensure_plans(c, par->gsize, prec, false)) return -1;
+  trace_mark("psb_mesh: FFT plans ready");
   if (deferred && bounds_finish(c, par)) return -1;
   trace_mark("psb_mesh: device drained, bounds checked");
   c->mesh_ready = true;

@@ -15,6 +15,12 @@
 // Runtime knobs the reference fixes at compile time:
 //   POWSPEC_B200_PRECISION = 8 | 4   (the reference's -DSINGLE_PREC, Makefile:14)
 //   POWSPEC_B200_DEVICE    = CUDA device ordinal (default 0)
+//   POWSPEC_B200_DEVICES   = "0,1,2,3" / "0-7": ONE mesh x-slab-decomposed over these
+//                            devices (psb_group: one host thread per device inside the
+//                            library, peer copies / peer stores, no NCCL) — how this
+//                            single-process C host runs meshes that exceed one GPU
+//                            (BASELINE configs 4 and 5).  Simulation boxes; a survey or a
+//                            pending coordinate conversion falls back to the first device.
 //   POWSPEC_B200_TIMING    = path: write a JSON line with the device stage timings
 //                            (CUDA events) of the run; never touches the output file
 
@@ -29,6 +35,28 @@
 #define P_ERR(...) fprintf(stderr, "\n\x1B[31;1mError:\x1B[0m " __VA_ARGS__)
 
 static psb_context *g_ctx = nullptr;
+static psb_group *g_group = nullptr;      // POWSPEC_B200_DEVICES: the slab-decomposed path
+
+// "0,1,2" and ranges "0-3" (also mixed); a device may be listed more than once
+static int parse_devices(const char *s, int *dev, int maxn) {
+  int n = 0;
+  while (s && *s && n < maxn) {
+    char *end = nullptr;
+    const long a = strtol(s, &end, 10);
+    if (end == s || a < 0) return -1;
+    long b = a;
+    s = end;
+    if (*s == '-') {
+      b = strtol(s + 1, &end, 10);
+      if (end == s + 1 || b < a) return -1;
+      s = end;
+    }
+    for (long d = a; d <= b && n < maxn; d++) dev[n++] = (int) d;
+    if (*s == ',') s++;
+    else if (*s) return -1;
+  }
+  return n;
+}
 
 // Coordinate conversion requested through cnvt_coord() below: carried out on the
 // device by the next genr_mesh(), on the records it uploads anyway.
@@ -117,8 +145,23 @@ psb_ref_MESH *genr_mesh(const psb_ref_CONF *conf, psb_ref_CATA *cat) {
 
   psb_params par;
   fill_params(conf, &par);
-  if (!g_ctx) g_ctx = psb_create(par.device);
-  if (!g_ctx) return nullptr;
+  int devs[16], ndev = 0;
+  if (const char *list = getenv("POWSPEC_B200_DEVICES")) {
+    ndev = parse_devices(list, devs, 16);
+    if (ndev < 0) { P_ERR("invalid POWSPEC_B200_DEVICES: `%s'\n", list); return nullptr; }
+    if (ndev >= 1) par.device = devs[0];
+  }
+  const bool slabs = ndev >= 2 && conf->issim && !g_cnvt.pending;
+  if (ndev >= 2 && !slabs && conf->verbose)
+    printf("  POWSPEC_B200_DEVICES: surveys run on one device (%d)\n", par.device);
+  if (slabs) {
+    if (!g_group) g_group = psb_group_create(devs, ndev);
+    if (!g_group) return nullptr;
+  }
+  else {
+    if (!g_ctx) g_ctx = psb_create(par.device);
+    if (!g_ctx) return nullptr;
+  }
 
   psb_cats in;
   memset(&in, 0, sizeof in);
@@ -138,7 +181,7 @@ psb_ref_MESH *genr_mesh(const psb_ref_CONF *conf, psb_ref_CATA *cat) {
     in.cnvt = &g_cnvt.cosmo;
     for (int i = 0; i < 2; i++) { in.dcnvt[i] = g_cnvt.dcnvt[i]; in.rcnvt[i] = g_cnvt.rcnvt[i]; }
   }
-  const int mesh_rc = psb_mesh(g_ctx, &par, &in);
+  const int mesh_rc = slabs ? psb_group_mesh(g_group, &par, &in) : psb_mesh(g_ctx, &par, &in);
   if (g_cnvt.pending) {
     free(g_cnvt.z); free(g_cnvt.d);
     g_cnvt.z = g_cnvt.d = nullptr;
@@ -158,7 +201,10 @@ psb_ref_MESH *genr_mesh(const psb_ref_CONF *conf, psb_ref_CATA *cat) {
   mesh->assign = conf->assign;
   mesh->fft_init = false;
   /* box metadata as def_box leaves it, read by save_res (src/save_res.c:70-82) */
-  psb_mesh_box(g_ctx, mesh->min, mesh->bsize, mesh->max);
+  if (slabs) {                  /* def_box for simulation boxes, src/genr_mesh.c:516-522 */
+    for (int a = 0; a < 3; a++) { mesh->min[a] = 0; mesh->bsize[a] = mesh->max[a] = conf->bsize[a]; }
+  }
+  else psb_mesh_box(g_ctx, mesh->min, mesh->bsize, mesh->max);
   if (conf->issim) {            /* src/genr_mesh.c:904-909 */
     for (int i = 0; i < cat->num; i++) {
       const double vol = mesh->bsize[0] * mesh->bsize[1] * mesh->bsize[2];
@@ -221,6 +267,7 @@ int cnvt_coord(const psb_ref_CONF *conf, psb_ref_CATA *cat) {
 void mesh_destroy(psb_ref_MESH *mesh) {
   /* device buffers and cuFFT plans live in the context */
   if (g_ctx) { psb_destroy(g_ctx); g_ctx = nullptr; }
+  if (g_group) { psb_group_destroy(g_group); g_group = nullptr; }
   free(mesh);
 }
 
@@ -230,11 +277,11 @@ psb_ref_PK *powspec(const psb_ref_CONF *conf, const psb_ref_CATA *cat, psb_ref_M
   if (conf->verbose) printf("\n");
   fflush(stdout);
   if (!cat) { P_ERR("catalogs not read\n"); return nullptr; }
-  if (!mesh || !g_ctx) { P_ERR("meshes not generated\n"); return nullptr; }
+  if (!mesh || !(g_ctx || g_group)) { P_ERR("meshes not generated\n"); return nullptr; }
 
   psb_params par;
   fill_params(conf, &par);
-  psb_result *res = psb_power(g_ctx, &par);
+  psb_result *res = g_group ? psb_group_power(g_group, &par) : psb_power(g_ctx, &par);
   if (!res) return nullptr;
 
   psb_ref_PK *pk = static_cast<psb_ref_PK *>(calloc(1, sizeof *pk));
@@ -284,7 +331,20 @@ psb_ref_PK *powspec(const psb_ref_CONF *conf, const psb_ref_CATA *cat, psb_ref_M
     static const char *names[] = {"h2d", "bounds", "sort", "memset", "assign", "fft", "geom", "bin", "ylm",
       "fft_strided", "cnvt"};
     double ms[PSB_T_COUNT];
-    if (*tpath && psb_timings(g_ctx, ms, PSB_T_COUNT) > 0) {
+    if (*tpath && g_group) {
+      // slab-decomposed run: the stage times of rank 0 (CUDA events), ms
+      static const char *dn[] = {"route", "assign", "halo", "fft_zy", "transpose", "fft_x", "bin", "reduce"};
+      double dm[PSB_D_COUNT];
+      if (psb_dist_timings(psb_group_rank(g_group, 0), dm, PSB_D_COUNT) >= 0) {
+        if (FILE *f = fopen(tpath, "a")) {
+          fprintf(f, "{\"grid\": %d, \"devices\": %d, \"stages_ms\": {", conf->gsize, psb_group_size(g_group));
+          for (int i = 0; i < PSB_D_COUNT; i++) fprintf(f, "%s\"%s\": %.4f", i ? ", " : "", dn[i], dm[i]);
+          fprintf(f, "}}\n");
+          fclose(f);
+        }
+      }
+    }
+    else if (*tpath && psb_timings(g_ctx, ms, PSB_T_COUNT) > 0) {
       if (FILE *f = fopen(tpath, "a")) {
         fprintf(f, "{\"grid\": %d, \"launches\": %ld, \"stages_ms\": {", conf->gsize, psb_launch_count(g_ctx));
         for (int i = 0; i < 11; i++) fprintf(f, "%s\"%s\": %.4f", i ? ", " : "", names[i], ms[i]);

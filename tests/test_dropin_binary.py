@@ -87,6 +87,59 @@ VERBOSE = F
         _compare(tmp_path / f"ref_{t}.txt", tmp_path / f"our_{t}.txt")
 
 
+@pytest.mark.parametrize("devices", ["0,0", "0-1", "0,0,0,0"])
+def test_sim_over_several_devices(tmp_path, devices):
+    """POWSPEC_B200_DEVICES: the reference's single-process host drives ONE mesh
+    slab-decomposed over several (here also virtual: a device listed twice) ranks through
+    the same genr_mesh() / powspec() seam — route, halo, distributed FFT with peer stores,
+    reduction inside the library (csrc/dist.cu psb_group).  Same files as the
+    all-reference binary."""
+    _need_binaries()
+    import torch
+    ranks = []
+    for part in devices.split(","):
+        a, _, b = part.partition("-")
+        ranks += list(range(int(a), int(b or a) + 1))
+    if torch.cuda.device_count() < 1 + max(ranks):
+        pytest.skip(f"needs {1 + max(ranks)} GPUs")
+    rng = np.random.default_rng(33)
+    for tag, n in (("a", 5000), ("b", 3500)):
+        np.savetxt(tmp_path / f"cat_{tag}.txt", np.c_[rng.random((n, 3)) * 300.0, rng.uniform(0.5, 2, n)],
+                   fmt="%.17g")
+    (tmp_path / "sim.conf").write_text("""
+DATA_CATALOG = [cat_a.txt, cat_b.txt]
+DATA_FORMATTER = ["%lf %lf %lf %lf", "%lf %lf %lf %lf"]
+DATA_POSITION = [$1,$2,$3,$1,$2,$3]
+DATA_WT_COMP = [$4, $4]
+CUBIC_SIM = T
+LINE_OF_SIGHT = [0,0,1]
+BOX_SIZE = 300
+GRID_SIZE = 48
+PARTICLE_ASSIGN = 2
+GRID_INTERLACE = T
+MULTIPOLE = [0,2,4]
+KMIN = 0
+BIN_SIZE = 0.04
+OVERWRITE = 1
+VERBOSE = F
+""")
+    _run(REF_BIN, "sim.conf", ["-a", "[ref_a.txt,ref_b.txt]", "-x", "ref_x.txt"], tmp_path, 4)
+    env_add = {"POWSPEC_B200_DEVICES": devices, "POWSPEC_B200_TIMING": str(tmp_path / "timing.jsonl")}
+    os.environ.update(env_add)
+    try:
+        out = _run(OUR_BIN, "sim.conf", ["-a", "[our_a.txt,our_b.txt]", "-x", "our_x.txt"], tmp_path, 4)
+    finally:
+        for k in env_add:
+            del os.environ[k]
+    assert "Generating meshes for FFT" in out and "Evaluating power spectra" in out
+    import json
+    rec = json.loads((tmp_path / "timing.jsonl").read_text().splitlines()[-1])
+    assert rec["grid"] == 48 and rec["devices"] == len(ranks)
+    assert rec["stages_ms"]["assign"] > 0 and rec["stages_ms"]["fft_x"] > 0
+    for t in ("a", "b", "x"):
+        _compare(tmp_path / f"ref_{t}.txt", tmp_path / f"our_{t}.txt")
+
+
 def test_survey_with_randoms_and_fkp(tmp_path):
     _need_binaries()
 
