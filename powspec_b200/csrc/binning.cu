@@ -75,10 +75,14 @@ __device__ __forceinline__ int bin_of(const BinGeom &g, const double *edges, dou
 template <int NV>
 __device__ __forceinline__ void warp_bin_add(int key, double (&v)[NV], double *bins,
     int nbin, int lane) {
+  // keys are non-decreasing along the used lanes, so once no lane finds its own key `off`
+  // lanes below, every segment is shorter than `off` and the remaining steps would add
+  // nothing: leave (warp-uniform).  Most rows have segments of 2-4 lanes.
 #pragma unroll
   for (int off = 1; off < 32; off <<= 1) {
     const int kprev = __shfl_up_sync(0xffffffffu, key, off);
     const bool take = (lane >= off) && (kprev == key);
+    if (__ballot_sync(0xffffffffu, take && key >= 0) == 0u) break;
 #pragma unroll
     for (int q = 0; q < NV; q++) {
       const double t = __shfl_up_sync(0xffffffffu, v[q], off);
