@@ -421,7 +421,13 @@ struct psb_dist {
   psb_slab sl;
   AssignGeom g;
   bool begun = false;
-  int want_p2p = 1;             // option: store the y pass straight into the peers' buffers
+  // The transposes: 1 = the y pass stores straight into the peers' buffers (FFT + transpose in
+  // one kernel), 0 = send layout + all-to-all on the second stream, overlapped with the next
+  // field's z / y passes, -1 = choose: measured on 8 B200 the SM-issued 128-byte peer stores
+  // sustain ~500 GB/s and stall the FFT kernel that issues them, the all-to-all 450-560 GB/s
+  // beside the compute — config 4: 262 ms with peer stores, 213 ms with the all-to-all; config
+  // 2: 12.8 vs 12.5 ms — while on 2 GPUs (half the data stays local) the fused kernel wins.
+  int want_p2p = -1;
   bool p2p = false;
   long runs = 0;
 
@@ -687,7 +693,8 @@ int setup_peers(psb_dist *d) {
   memcpy(d->peers_of, bufs, sizeof bufs);
   d->p2p = false;
   d->have_peers = true;
-  if (!d->want_p2p || d->nranks == 1) return 0;
+  const bool want = d->want_p2p < 0 ? (strcmp(d->tr->name(), "nccl") != 0 || d->nranks <= 2) : d->want_p2p != 0;
+  if (!want || d->nranks == 1) return 0;
   bool ok = true;
   for (int b = 0; b < 5; b++) {
     for (int q = 0; q < FftOut::MAXB; q++) d->peer_base[b][q] = nullptr;

@@ -1,7 +1,14 @@
-T="timeout 400 python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
-$T --nproc-per-node 8 --master-port 29501 bench.py --gpus 8 --steps 5 --warmup 3 > gpurun_out/r2s2_c2_8gpu.json 2> gpurun_out/r2s2_c2_8gpu.err
-$T --nproc-per-node 4 --master-port 29502 bench.py --gpus 4 --steps 5 --warmup 3 --no-replicas > gpurun_out/r2s2_c2_4gpu.json 2> gpurun_out/r2s2_c2_4gpu.err
-$T --nproc-per-node 8 --master-port 29503 bench.py --gpus 8 --workload c4 --steps 2 --warmup 3 > gpurun_out/r2s2_c4_8gpu.json 2> gpurun_out/r2s2_c4_8gpu.err
-$T --nproc-per-node 8 --master-port 29504 bench.py --gpus 8 --workload c5 --precision 4 --steps 2 --warmup 3 > gpurun_out/r2s2_c5_8gpu.json 2> gpurun_out/r2s2_c5_8gpu.err
-timeout 300 python -m pytest tests/test_gpu_multi.py tests/test_gpu_group.py -m gpu -q 2>&1 | tail -4
-for f in c2_8gpu c2_4gpu c4_8gpu c5_8gpu; do echo $f; tail -c 600 gpurun_out/r2s2_$f.json; tail -3 gpurun_out/r2s2_$f.err; done
+T="timeout 300 python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1"
+run() { name=$1; np=$2; port=$3; shift 3
+  $T --nproc-per-node $np --master-port $port bench.py --gpus $np "$@" > gpurun_out/r2s3_$name.json 2> gpurun_out/r2s3_$name.err
+  python - <<EOF
+import json
+try:
+    d=json.loads([l for l in open("gpurun_out/r2s3_$name.json") if l.startswith("{")][-1])
+    print("$name", round(d["ms_per_step"],2), {k:round(v,2) for k,v in d["stages_ms_max_over_ranks"].items()}, "nvlink", round(d["nvlink"]["frac"],3), d["nvlink"]["transport"][:20], "parity", d["parity"] and d["parity"]["ok"])
+except Exception as ex:
+    print("$name FAILED", ex); print(open("gpurun_out/r2s3_$name.err").read()[-800:])
+EOF
+}
+run c2_4gpu_auto 4 29503 --steps 5 --warmup 3 --no-replicas --no-e2e
+POWSPEC_B200_P2P=0 run c2_2gpu_nccl 2 29504 --steps 5 --warmup 3 --no-replicas --no-e2e
