@@ -18,8 +18,9 @@
  * (src/read_cata.h:42-59), MESH (src/genr_mesh.h:48-70) and PK
  * (src/multipole.h:38-61, built with -DOMP as the reference Makefile does,
  * Makefile:17).  They are prefixed psb_ref_ so that this header can be included
- * next to the reference's own headers; tests/test_refabi.py compiles a
- * translation unit that includes both and static-asserts every offset.
+ * next to the reference's own headers;
+ * tests/test_library_cpu.py::test_refabi_struct_layout_matches_reference_headers compiles a
+ * translation unit that includes both and static-asserts sizeof and every offset.
  * FFT_PLAN / FFT_REAL* / FFT_CMPLX* members are pointers in both precisions
  * (src/fftw_define.h:32-48), so one layout serves -DSINGLE_PREC as well.
  */

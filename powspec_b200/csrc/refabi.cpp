@@ -231,8 +231,11 @@ psb_ref_MESH *genr_mesh(const psb_ref_CONF *conf, psb_ref_CATA *cat) {
 // the request, reads the distance table if one is named, and leaves the
 // conversion itself to genr_mesh(), which performs it on the device on the
 // records it uploads (the host arrays keep RA / Dec / z; genr_mesh frees them).
-// A negative redshift or a failed convergence test is therefore reported by
-// genr_mesh (POWSPEC_ERR_MESH) instead of here (POWSPEC_ERR_CNVT).
+// What can FAIL is checked here, on the host, so that the reference's error contract
+// holds (message + POWSPEC_ERR_CNVT from cnvt_coord(), src/cnvt_coord.c:549-582, before any
+// "DONE" is printed): negative / invalid redshifts (:185-268), the convergence test of
+// the Legendre-Gauss order on the catalogues' redshift range (:356-396, :495-511), a table
+// that cannot be interpolated (:453-456).
 int cnvt_coord(const psb_ref_CONF *conf, psb_ref_CATA *cat) {
   if (!conf) { P_ERR("configuration parameters not loaded\n"); return -10; /* POWSPEC_ERR_CONF */ }
   if (!conf->cnvt) return 0;
@@ -257,6 +260,39 @@ int cnvt_coord(const psb_ref_CONF *conf, psb_ref_CATA *cat) {
   for (int i = 0; i < cat->num && i < 2; i++) {
     g_cnvt.dcnvt[i] = conf->dcnvt ? conf->dcnvt[i] : 0;     /* DEFAULT_CONVERT = false */
     g_cnvt.rcnvt[i] = conf->rcnvt ? conf->rcnvt[i] : 0;
+  }
+  auto drop_table = [&]() { free(g_cnvt.z); free(g_cnvt.d); g_cnvt.z = g_cnvt.d = nullptr; };
+  if (conf->fcdst) {
+    if (g_cnvt.cosmo.nsample < 2) {
+      P_ERR("failed to interpolate the sample points\n");
+      drop_table();
+      return -12;
+    }
+  }
+  else {
+    // redshift range of everything that will be converted (cnvt_z_sample)
+    double zmin = 1.7976931348623157e308, zmax = -1.7976931348623157e308;
+    for (int i = 0; i < cat->num && i < 2; i++)
+      for (int r = 0; r < 2; r++) {
+        const psb_ref_DATA *p = r ? (cat->rand ? cat->rand[i] : nullptr) : (cat->data ? cat->data[i] : nullptr);
+        const size_t n = r ? (cat->nrand ? cat->nrand[i] : 0) : cat->ndata[i];
+        if (!(r ? g_cnvt.rcnvt[i] : g_cnvt.dcnvt[i]) || !p) continue;
+        for (size_t k = 0; k < n; k++) {
+          const double z = p[k].x[2];
+          if (z < 0) {
+            P_ERR("invalid negative redshift in the %s catalog:\n(%g, %g, %g)\n", r ? "random" : "data",
+                p[k].x[0], p[k].x[1], z);
+            return -12;
+          }
+          if (zmax < z) zmax = z;
+          if (zmin > z) zmin = z;
+        }
+      }
+    if (zmin > zmax) { P_ERR("invalid redshift value in the catalogs\n"); return -12; }
+    if (psb_cnvt_order(&g_cnvt.cosmo, zmin, zmax) < 0) {
+      P_ERR("failed to perform the convergency test for integrations\n");
+      return -12;
+    }
   }
   g_cnvt.pending = true;
   if (conf->verbose) printf("  Conversion scheduled on the device (with the mesh generation)\n");

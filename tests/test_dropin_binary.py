@@ -232,3 +232,17 @@ VERBOSE = F
     assert "Converting coordinates" in out
     _compare(tmp_path / "ref.txt", tmp_path / "our.txt")
     _compare(tmp_path / "ref.txt", tmp_path / "our_dev.txt")
+
+    # error contract of the seam's cnvt_coord (src/cnvt_coord.c:185-268, 549-582): a negative
+    # redshift is reported by the conversion step itself — message on stderr, the host's
+    # [FAIL] path, non-zero exit — not later by genr_mesh
+    bad = cat(5, 3000)
+    bad[17, 2] = -0.25
+    np.savetxt(tmp_path / "data.txt", bad, fmt="%.17g")
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    for binary in (REF_BIN, OUR_BIN_CNVT):
+        p = subprocess.run([binary, "-c", "sky.conf", "-a", "bad.txt"], cwd=tmp_path, env=env,
+                           capture_output=True, text=True)
+        assert p.returncode != 0
+        assert "invalid negative redshift in the data catalog" in p.stderr
+        assert "Generating meshes for FFT" not in p.stdout
