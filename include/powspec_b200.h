@@ -169,6 +169,10 @@ long psb_launch_count(const psb_context *ctx);
 void *psb_stream(const psb_context *ctx);
 /* the scatter the last psb_mesh used: 0 = global reductions, 1 = owner-computes tiles */
 int psb_assign_path(const psb_context *ctx);
+/* owner-computes path: list entries of the last dense chunk that did not fit their tile's
+ * slots and were added through the overflow list (0 for catalogues near uniform on the tile
+ * scale; -1 without a context) */
+long psb_tile_overflow(const psb_context *ctx);
 
 /* Tunables (tests / ablations; the list is in psb_set_option, csrc/context.cu):
  * "sort", "strip", "coop", "owner", "own_fft", "fft_fused", "stream", "stream_chunk",

@@ -130,6 +130,8 @@ def load_library():
     L.psb_launch_count.argtypes = [C.c_void_p]
     L.psb_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_long]
     L.psb_assign_path.argtypes = [C.c_void_p]
+    L.psb_tile_overflow.restype = C.c_long
+    L.psb_tile_overflow.argtypes = [C.c_void_p]
     L.psb_stream.restype = C.c_void_p
     L.psb_stream.argtypes = [C.c_void_p]
     L.psb_generate_catalog.restype = C.c_void_p

@@ -1,9 +1,10 @@
 // Owner-computes mass assignment for sm_100a (the "cell-sorted batches in shared memory"
 // formulation of the assignment loops of src/genr_mesh.c:50-412, 793-858):
 //
-//   1. k_tile_lists<count> / scan / k_tile_lists<fill>: every particle is appended to the
-//      list of every mesh TILE (16 x 16 x 32 cells) that the stencils of its fields reach
-//      — 1.46 entries per particle for TSC + interlacing;
+//   1. k_tile_lists: every particle is appended to the list of every mesh TILE (16 x 16 x 32
+//      cells) that the stencils of its fields reach — 1.46 entries per particle for TSC +
+//      interlacing — either in ONE pass into fixed-capacity slots (with an overflow list for
+//      the rare entry that does not fit, k_tile_overflow) or by count / scan / fill;
 //   2. k_tile_accumulate: one block per (tile, field) keeps the tile in shared memory as
 //      FIXED-POINT numbers in two 32-bit limbs and adds the in-tile part of each listed
 //      particle's stencil with the native shared-memory ATOMS.ADD — the only shared atomic
@@ -37,6 +38,7 @@
 
 #include <cuda.h>      // CUtensorMap (types only: the encoder is looked up at run time)
 
+#include <algorithm>
 #include <cfloat>
 #include <cstring>
 
@@ -122,27 +124,48 @@ __device__ __forceinline__ TileSet tile_set(double2 a, double2 b, const AssignGe
   return ts;
 }
 
+// One-pass lists: every tile owns `cap` slots (no count pass, no scan); what does not fit
+// goes to a global overflow list of (record, tile) that a small kernel adds to the mesh
+// after the tiles have been stored.
+struct OnePass {
+  uint32_t cap = 0;             // slots per tile; 0: exact lists (count + scan + fill)
+  uint32_t ovcap = 0;
+  uint32_t *ovcount = nullptr;
+  double2 *ovrec = nullptr;
+  uint32_t *ovtile = nullptr;
+};
+
+__device__ __forceinline__ void put_entry(const OnePass &op, double2 *__restrict__ out, uint32_t tile, uint32_t pos,
+    double2 a, double2 b) {
+  if (op.cap == 0u) { st_record(out, pos, a, b); return; }
+  if (pos < op.cap) { st_record(out, (size_t) tile * op.cap + pos, a, b); return; }
+  const uint32_t q = atomicAdd(op.ovcount, 1u);
+  if (q < op.ovcap) { st_record(op.ovrec, q, a, b); op.ovtile[q] = tile; }
+}
+
 // the up to seven further tiles of a particle that straddles tile faces
 template <bool FILL>
 __device__ __forceinline__ void tile_extra(const TileSet &ts, uint32_t *__restrict__ cnt_or_cursor,
-    double2 *__restrict__ out, double2 a, double2 b) {
+    double2 *__restrict__ out, double2 a, double2 b, const OnePass &op) {
 #pragma unroll
   for (int m = 1; m < 8; m++) {
     if (((m & 1) && !ts.step[2]) || ((m & 2) && !ts.step[1]) || ((m & 4) && !ts.step[0])) continue;
     const uint32_t tile = ts.first + ((m & 1) ? ts.step[2] : 0u) + ((m & 2) ? ts.step[1] : 0u) +
         ((m & 4) ? ts.step[0] : 0u);
     const uint32_t pos = atomicAdd(cnt_or_cursor + tile, 1u);
-    if (FILL) st_record(out, pos, a, b);
+    if (FILL) put_entry(op, out, tile, pos, a, b);
   }
 }
 
-// FILL = false: count the list lengths (and, optionally, the coordinate bounds and the
-// largest |weight| of the block's particles); FILL = true: write the records.  The fill
-// pass waits for the returned list positions: UNROLL particles per thread are in flight.
-template <int SCHEME, bool INTERLACE, bool FILL, int UNROLL>
+// FILL = false: count the list lengths; FILL = true: write the records (exact lists: into
+// the slots the scan of the counts assigned; one-pass lists: into the tile's own slots,
+// counting as it goes).  The coordinate bounds and the largest |weight| of the block's
+// particles are reduced by whichever pass comes first (STATS).  The fill pass waits for the
+// returned list positions: UNROLL particles per thread are in flight.
+template <int SCHEME, bool INTERLACE, bool FILL, int UNROLL, bool STATS>
 __global__ void __launch_bounds__(256) k_tile_lists(const double2 *__restrict__ p, size_t n, AssignGeom g,
     uint32_t *__restrict__ cnt_or_cursor, double2 *__restrict__ out, double *__restrict__ partials,
-    double *__restrict__ wmax_part) {
+    double *__restrict__ wmax_part, OnePass op) {
   const TileDims td = tile_dims(g.ng);
   const double scale[3] = {(double) g.ng / g.len[0], (double) g.ng / g.len[1], (double) g.ng / g.len[2]};
   double lo3[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi3[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX}, wm = 0.0;
@@ -160,7 +183,7 @@ __global__ void __launch_bounds__(256) k_tile_lists(const double2 *__restrict__ 
 #pragma unroll
     for (int u = 0; u < UNROLL; u++) {
       if (i0 + u * stride >= n) continue;
-      if (!FILL) {
+      if (STATS) {
         lo3[0] = fmin(lo3[0], a[u].x); hi3[0] = fmax(hi3[0], a[u].x);
         lo3[1] = fmin(lo3[1], a[u].y); hi3[1] = fmax(hi3[1], a[u].y);
         lo3[2] = fmin(lo3[2], b[u].x); hi3[2] = fmax(hi3[2], b[u].x);
@@ -173,15 +196,15 @@ __global__ void __launch_bounds__(256) k_tile_lists(const double2 *__restrict__ 
     if (FILL) {
 #pragma unroll
       for (int u = 0; u < UNROLL; u++)
-        if (i0 + u * stride < n) st_record(out, pos[u], a[u], b[u]);
+        if (i0 + u * stride < n) put_entry(op, out, ts[u].first, pos[u], a[u], b[u]);
     }
     if (more) {
 #pragma unroll
       for (int u = 0; u < UNROLL; u++)
-        if (i0 + u * stride < n) tile_extra<FILL>(ts[u], cnt_or_cursor, out, a[u], b[u]);
+        if (i0 + u * stride < n) tile_extra<FILL>(ts[u], cnt_or_cursor, out, a[u], b[u], op);
     }
   }
-  if (FILL) return;
+  if (!STATS) return;
   __shared__ double s[7][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -355,7 +378,7 @@ struct TileMaps { CUtensorMap m[2]; };
 template <int SCHEME, typename real, int NFIELD, int MODE, bool TMA>
 __global__ void __launch_bounds__(ACC_THREADS, ACC_BLOCKS) k_tile_accumulate(const double2 *__restrict__ parts,
     const uint32_t *__restrict__ start, AssignGeom g, double wscale, const double *__restrict__ wmax_dev,
-    real *__restrict__ mesh0, real *__restrict__ mesh1, const __grid_constant__ TileMaps maps) {
+    real *__restrict__ mesh0, real *__restrict__ mesh1, const __grid_constant__ TileMaps maps, uint32_t cap) {
   extern __shared__ __align__(1024) uint32_t sm[];      // cell c: words 2c, 2c + 1 = its limbs (limb_swap)
   __shared__ uint16_t queue[BATCH];             // listed particles (index in the batch) that straddle the tile's z faces
   __shared__ uint32_t nqueue;
@@ -371,7 +394,9 @@ __global__ void __launch_bounds__(ACC_THREADS, ACC_BLOCKS) k_tile_accumulate(con
   for (uint32_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
     const int tz = tile % td.ntz, ty = (tile / td.ntz) % td.nty, tx = tile / (td.ntz * td.nty);
     const int x0 = tx * TX, y0 = ty * TY, z0 = tz * TZ;
-    const uint32_t b0 = start[tile], np = start[tile + 1] - b0;
+    // exact lists: offsets from the scan; one-pass lists: `cap` slots per tile, start[] = lengths
+    const uint32_t b0 = cap ? 0u : start[tile], np = cap ? min(start[tile], cap) : start[tile + 1] - b0;
+    const size_t lbase = cap ? (size_t) tile * cap : (size_t) b0;
     // headroom: a cell receives at most one contribution per listed particle; the high
     // limb stays below 2^30 for 2^30 / 2^(S - LOBITS) contributions of the largest size
     int S = 43;
@@ -384,12 +409,12 @@ __global__ void __launch_bounds__(ACC_THREADS, ACC_BLOCKS) k_tile_accumulate(con
       for (uint32_t base = 0; base < np; base += BATCH) {
         const uint32_t lim = min(np, base + BATCH);
         for (uint32_t j = base + threadIdx.x; j < lim; j += ACC_THREADS)
-          if (tile_add<SCHEME, false>(parts, (size_t) b0 + j, f, g, wnorm, x0, y0, z0, sm_lo))
+          if (tile_add<SCHEME, false>(parts, lbase + j, f, g, wnorm, x0, y0, z0, sm_lo))
             queue[atomicAdd(&nqueue, 1u)] = (uint16_t) (j - base);
         __syncthreads();
         const uint32_t nq = nqueue;
         for (uint32_t k = threadIdx.x; k < nq; k += ACC_THREADS)
-          tile_add<SCHEME, true>(parts, (size_t) b0 + base + queue[k], f, g, wnorm, x0, y0, z0, sm_lo);
+          tile_add<SCHEME, true>(parts, lbase + base + queue[k], f, g, wnorm, x0, y0, z0, sm_lo);
         __syncthreads();
         if (threadIdx.x == 0) nqueue = 0;
         if (lim < np) {
@@ -470,19 +495,76 @@ __global__ void __launch_bounds__(ACC_THREADS, ACC_BLOCKS) k_tile_accumulate(con
 
 int g_fill_unroll = 4;  // particles in flight per thread of the fill pass (psb_set_option "tile_fill_unroll")
 
+// One-pass lists: the entries that did not fit their tile's slots.  One thread per
+// (particle, tile) entry adds the in-tile part of the particle's stencils to the mesh with
+// global atomics — after the accumulation has stored (or added) the tiles.
+template <int SCHEME, typename real, int NFIELD>
+__global__ void __launch_bounds__(256) k_tile_overflow(const double2 *__restrict__ rec,
+    const uint32_t *__restrict__ tiles, uint32_t n, AssignGeom g, double wscale, real *__restrict__ mesh0,
+    real *__restrict__ mesh1) {
+  constexpr int NS = SCHEME + 1;
+  const TileDims td = tile_dims(g.ng);
+  const double ngd = (double) g.ng;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double2 a, b;
+    ld_record(rec, i, a, b);
+    const uint32_t tile = tiles[i];
+    const int x0 = (int) (tile / (uint32_t) (td.ntz * td.nty)) * TX, y0 = (int) ((tile / td.ntz) % td.nty) * TY,
+        z0 = (int) (tile % td.ntz) * TZ;
+    double pw = b.y * wscale;
+    if constexpr (SCHEME == 3) pw *= 0x1.2f684bda12f68p-8;
+#pragma unroll 1
+    for (int f = 0; f < NFIELD; f++) {
+      double x[3] = {a.x, a.y, b.x};
+      const double *org = f ? g.sorg : g.org;
+      if (f) {
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+          if (x[k] >= __dadd_rn(g.sorg[k], g.len[k])) x[k] = __dsub_rn(x[k], g.len[k]);
+      }
+      int ix[NS], iy[NS], iz[NS], cc;
+      double wx[NS], wy[NS], wz[NS], dd;
+      grid_split2(x[0], AxisXform{org[0], ngd, g.len[0], g.inv_len[0]}, cc, dd);
+      stencil_from<SCHEME>(cc, dd, g.ng, ix, wx);
+      grid_split2(x[1], AxisXform{org[1], ngd, g.len[1], g.inv_len[1]}, cc, dd);
+      stencil_from<SCHEME>(cc, dd, g.ng, iy, wy);
+      grid_split2(x[2], AxisXform{org[2], ngd, g.len[2], g.inv_len[2]}, cc, dd);
+      stencil_from<SCHEME>(cc, dd, g.ng, iz, wz);
+      real *m = f ? mesh1 : mesh0;
+#pragma unroll
+      for (int u = 0; u < NS; u++) {
+        if ((uint32_t) (ix[u] - x0) >= (uint32_t) TX) continue;
+        const double wxu = wx[u] * pw;
+#pragma unroll
+        for (int v = 0; v < NS; v++) {
+          if ((uint32_t) (iy[v] - y0) >= (uint32_t) TY) continue;
+          const double wxy = wxu * wy[v];
+          real *row = m + ((size_t) ix[u] * g.ng + iy[v]) * g.rowlen;
+#pragma unroll
+          for (int c = 0; c < NS; c++)
+            if ((uint32_t) (iz[c] - z0) < (uint32_t) TZ) atomicAdd(row + iz[c], (real) (wxy * wz[c]));
+        }
+      }
+    }
+  }
+}
+
+// mode 0: count (exact lists), 1: fill the slots the scan assigned, 2: one-pass fill
 template <int SCHEME, bool INTERLACE>
-int launch_lists(const double *p, size_t n, const AssignGeom &g, bool fill, uint32_t *cnt, double *out,
-    double *partials, double *wmax_part, cudaStream_t st) {
+int launch_lists(const double *p, size_t n, const AssignGeom &g, int mode, uint32_t *cnt, double *out,
+    double *partials, double *wmax_part, const OnePass &op, cudaStream_t st) {
   const double2 *pp = reinterpret_cast<const double2 *>(p);
   const int nblk = row_keys_blocks(n);
-  if (fill) {
-    double2 *o = reinterpret_cast<double2 *>(out);
-    if (g_fill_unroll >= 4) k_tile_lists<SCHEME, INTERLACE, true, 4><<<nblk, 256, 0, st>>>(pp, n, g, cnt, o, nullptr, nullptr);
-    else if (g_fill_unroll >= 2) k_tile_lists<SCHEME, INTERLACE, true, 2><<<nblk, 256, 0, st>>>(pp, n, g, cnt, o, nullptr, nullptr);
-    else k_tile_lists<SCHEME, INTERLACE, true, 1><<<nblk, 256, 0, st>>>(pp, n, g, cnt, o, nullptr, nullptr);
+  double2 *o = reinterpret_cast<double2 *>(out);
+  if (mode == 2)
+    k_tile_lists<SCHEME, INTERLACE, true, 4, true><<<nblk, 256, 0, st>>>(pp, n, g, cnt, o, partials, wmax_part, op);
+  else if (mode == 1) {
+    if (g_fill_unroll >= 4) k_tile_lists<SCHEME, INTERLACE, true, 4, false><<<nblk, 256, 0, st>>>(pp, n, g, cnt, o, nullptr, nullptr, op);
+    else if (g_fill_unroll >= 2) k_tile_lists<SCHEME, INTERLACE, true, 2, false><<<nblk, 256, 0, st>>>(pp, n, g, cnt, o, nullptr, nullptr, op);
+    else k_tile_lists<SCHEME, INTERLACE, true, 1, false><<<nblk, 256, 0, st>>>(pp, n, g, cnt, o, nullptr, nullptr, op);
   }
   else
-    k_tile_lists<SCHEME, INTERLACE, false, 2><<<nblk, 256, 0, st>>>(pp, n, g, cnt, nullptr, partials, wmax_part);
+    k_tile_lists<SCHEME, INTERLACE, false, 2, true><<<nblk, 256, 0, st>>>(pp, n, g, cnt, nullptr, partials, wmax_part, op);
   PSB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -520,7 +602,7 @@ int g_tile_tma = 1;     // ablation switch (psb_set_option "tile_tma")
 
 template <int SCHEME, typename real>
 int launch_accumulate(const double *parts, const uint32_t *start, const AssignGeom &g, double wscale,
-    const double *wmax, bool add, void *m0, void *m1, cudaStream_t st) {
+    const double *wmax, bool add, void *m0, void *m1, uint32_t cap, cudaStream_t st) {
   const size_t smem = (size_t) TCELLS * 8;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -536,7 +618,7 @@ int launch_accumulate(const double *parts, const uint32_t *start, const AssignGe
   do {                                                                                            \
     auto kern = k_tile_accumulate<SCHEME, real, NF, MODE, TMA>;                                   \
     PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
-    kern<<<ACC_BLOCKS * sms, ACC_THREADS, smem, st>>>(pp, start, g, wscale, wmax, a, b, maps);              \
+    kern<<<ACC_BLOCKS * sms, ACC_THREADS, smem, st>>>(pp, start, g, wscale, wmax, a, b, maps, cap);              \
   } while (0)
   if constexpr (sizeof(real) == 8) {
     if (tma) { if (m1) PSB_ACC(2, 0, true); else PSB_ACC(1, 0, true); }
@@ -567,6 +649,18 @@ bool tile_assign_supported(const AssignGeom &g) {
   return true;
 }
 
+// Slots per tile of the one-pass lists: 1.5 x the mean list length of a uniform catalogue
+// (every axis: a stencil range of r cells straddles a tile face with probability (r-1)/T)
+// + 64.  A Poisson tile of BASELINE config 2 (mean 1114) is 18 sigma below it; catalogues
+// clustered on the tile scale overflow, and the caller falls back to the exact lists.
+uint32_t tile_list_capacity(const AssignGeom &g, size_t n, int scheme, bool interlace) {
+  const double r = scheme + 1 + (interlace ? 1 : 0);
+  const TileDims td = tile_dims(g.ng);
+  const double dup = (1 + (r - 1) / TX) * (1 + (r - 1) / TY) * (1 + (r - 1) / TZ);
+  const double mean = (double) n * dup / ((double) td.ntx * td.nty * td.ntz);
+  return (uint32_t) std::min(4.0e9, 1.5 * mean + 64.0) & ~3u;
+}
+
 size_t tile_list_count(const AssignGeom &g) {
   const TileDims td = tile_dims(g.ng);
   return (size_t) td.ntx * td.nty * td.ntz;
@@ -579,8 +673,8 @@ int launch_tile_count(const double *p, size_t n, const AssignGeom &g, int scheme
     uint32_t *cnt, double *partials, double *wmax_part, double *wmax, cudaStream_t st) {
 #define PSB_LISTS(S)                                                                              \
   case S:                                                                                         \
-    if (interlace ? launch_lists<S, true>(p, n, g, false, cnt, nullptr, partials, wmax_part, st)  \
-                  : launch_lists<S, false>(p, n, g, false, cnt, nullptr, partials, wmax_part, st)) \
+    if (interlace ? launch_lists<S, true>(p, n, g, 0, cnt, nullptr, partials, wmax_part, OnePass{}, st)  \
+                  : launch_lists<S, false>(p, n, g, 0, cnt, nullptr, partials, wmax_part, OnePass{}, st)) \
       return -1;                                                                                  \
     break;
   switch (scheme) { PSB_LISTS(0) PSB_LISTS(1) PSB_LISTS(2) PSB_LISTS(3) default: return -1; }
@@ -595,20 +689,62 @@ int launch_tile_fill(const double *p, size_t n, const AssignGeom &g, int scheme,
     uint32_t *cursor, double *lists, cudaStream_t st) {
 #define PSB_LISTS(S)                                                                              \
   case S:                                                                                         \
-    return interlace ? launch_lists<S, true>(p, n, g, true, cursor, lists, nullptr, nullptr, st)  \
-                     : launch_lists<S, false>(p, n, g, true, cursor, lists, nullptr, nullptr, st);
+    return interlace ? launch_lists<S, true>(p, n, g, 1, cursor, lists, nullptr, nullptr, OnePass{}, st)  \
+                     : launch_lists<S, false>(p, n, g, 1, cursor, lists, nullptr, nullptr, OnePass{}, st);
   switch (scheme) { PSB_LISTS(0) PSB_LISTS(1) PSB_LISTS(2) PSB_LISTS(3) default: return -1; }
 #undef PSB_LISTS
 }
 
+// One-pass lists (no count pass, no scan): cnt = tile_list_count zeroed counters (left holding
+// the list lengths, possibly beyond the capacity), lists = tile_list_count * op.cap records;
+// *op.ovcount (zeroed by the caller) counts the entries that did not fit.  Also reduces the
+// coordinate bounds (optional) and max |w| like launch_tile_count.
+int launch_tile_fill_onepass(const double *p, size_t n, const AssignGeom &g, int scheme, bool interlace,
+    uint32_t *cnt, double *lists, const TileOnePass &t, double *partials, double *wmax_part, double *wmax,
+    cudaStream_t st) {
+  OnePass op;
+  op.cap = t.cap; op.ovcap = t.ovcap; op.ovcount = t.ovcount;
+  op.ovrec = reinterpret_cast<double2 *>(t.ovrec); op.ovtile = t.ovtile;
+#define PSB_LISTS(S)                                                                              \
+  case S:                                                                                         \
+    if (interlace ? launch_lists<S, true>(p, n, g, 2, cnt, lists, partials, wmax_part, op, st)    \
+                  : launch_lists<S, false>(p, n, g, 2, cnt, lists, partials, wmax_part, op, st))  \
+      return -1;                                                                                  \
+    break;
+  switch (scheme) { PSB_LISTS(0) PSB_LISTS(1) PSB_LISTS(2) PSB_LISTS(3) default: return -1; }
+#undef PSB_LISTS
+  k_wmax_reduce<<<1, 32, 0, st>>>(wmax_part, row_keys_blocks(n), wmax);
+  PSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_tile_overflow(const double *ovrec, const uint32_t *ovtile, uint32_t n, const AssignGeom &g, int scheme,
+    int precision, double wscale, void *mesh0, void *mesh1, cudaStream_t st) {
+  if (!n) return 0;
+  const double2 *r = reinterpret_cast<const double2 *>(ovrec);
+  const int grid = (int) std::min<uint32_t>((n + 255) / 256, 148 * 8);
+#define PSB_OV(S, T)                                                                              \
+  do {                                                                                            \
+    if (mesh1) k_tile_overflow<S, T, 2><<<grid, 256, 0, st>>>(r, ovtile, n, g, wscale, (T *) mesh0, (T *) mesh1); \
+    else k_tile_overflow<S, T, 1><<<grid, 256, 0, st>>>(r, ovtile, n, g, wscale, (T *) mesh0, (T *) nullptr);    \
+  } while (0)
+#define PSB_OVS(S) case S: if (precision == 8) PSB_OV(S, double); else PSB_OV(S, float); break;
+  switch (scheme) { PSB_OVS(0) PSB_OVS(1) PSB_OVS(2) PSB_OVS(3) default: return -1; }
+#undef PSB_OVS
+#undef PSB_OV
+  PSB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // start: tile_list_count + 1 offsets into lists; add: the meshes already hold data
 int launch_tile_accumulate(const double *lists, const uint32_t *start, const AssignGeom &g, int scheme,
-    int precision, double wscale, const double *wmax, bool add, void *mesh0, void *mesh1, cudaStream_t st) {
+    int precision, double wscale, const double *wmax, bool add, void *mesh0, void *mesh1, cudaStream_t st,
+    uint32_t cap) {
 #define PSB_DISPATCH(S)                                                                           \
   case S:                                                                                         \
     return precision == 8                                                                         \
-        ? launch_accumulate<S, double>(lists, start, g, wscale, wmax, add, mesh0, mesh1, st)      \
-        : launch_accumulate<S, float>(lists, start, g, wscale, wmax, add, mesh0, mesh1, st);
+        ? launch_accumulate<S, double>(lists, start, g, wscale, wmax, add, mesh0, mesh1, cap, st) \
+        : launch_accumulate<S, float>(lists, start, g, wscale, wmax, add, mesh0, mesh1, cap, st);
   switch (scheme) {
     PSB_DISPATCH(0) PSB_DISPATCH(1) PSB_DISPATCH(2) PSB_DISPATCH(3)
     default: set_error("unrecognised particle assignment scheme: %d\n", scheme); return -1;

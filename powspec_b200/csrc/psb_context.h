@@ -82,6 +82,10 @@ struct psb_context {
   cudaEvent_t ev_filled[2] = {nullptr, nullptr}, ev_consumed[2] = {nullptr, nullptr};
   DevBuf sorted, keys, hist, cursor, cubtmp, bounds_part;
   DevBuf tile_cnt, tile_start, wmax_buf;  // owner-computes assignment: list counts / offsets, max |w|
+  DevBuf tile_ovrec, tile_ovtile;         // one-pass lists: overflow entries (records, tile indices + counter)
+  size_t tile_scan_bytes = 0;
+  int tile_onepass_backoff = 0;           // dense chunks left that go straight to the exact lists
+  uint32_t tile_overflowed = 0;           // overflow entries of the last dense chunk
   int assign_path = 0;                  // what the last scatter used: 0 global reductions, 1 owner-computes tiles
   size_t bounds_used = 0;               // bytes of bounds_part holding deferred bounds partials
   void *pinned[2] = {nullptr, nullptr};
@@ -115,6 +119,9 @@ struct psb_context {
   long opt_sort = 1;
   long opt_sort_min = 1 << 16;
   long opt_geom_sym = 1;                // fold +-n_x, +-n_y in the mode-counting pass
+  long opt_tile_onepass = 1;            // tile lists in one pass (fixed capacity + overflow list)
+  long opt_tile_cap = 0;                // > 0: slots per tile (tests: forces overflow)
+  long opt_tile_ovcap = 0;              // > 0: room of the overflow list (tests: forces the fallback)
   long opt_owner = -1;                  // owner-computes tile assignment: 1 / 0 / -1 = when the chunk is dense
                                         // enough to pay for writing every mesh cell (>= Ntot / 32 particles)
   long opt_coop = 1;                    // z-coalesced scatter kernel

@@ -68,8 +68,23 @@ int launch_tile_count(const double *p, size_t n, const AssignGeom &g, int scheme
     uint32_t *cnt, double *partials, double *wmax_part, double *wmax, cudaStream_t st);
 int launch_tile_fill(const double *p, size_t n, const AssignGeom &g, int scheme, bool interlace,
     uint32_t *cursor, double *lists, cudaStream_t st);
+// cap > 0: one-pass lists (cap slots per tile, start[] holds the list lengths)
 int launch_tile_accumulate(const double *lists, const uint32_t *start, const AssignGeom &g, int scheme,
-    int precision, double wscale, const double *wmax, bool add, void *mesh0, void *mesh1, cudaStream_t st);
+    int precision, double wscale, const double *wmax, bool add, void *mesh0, void *mesh1, cudaStream_t st,
+    uint32_t cap = 0);
+// one-pass lists: fixed capacity per tile, overflow list (assign_tiles.cu)
+struct TileOnePass {
+  uint32_t cap = 0, ovcap = 0;
+  uint32_t *ovcount = nullptr;  // device counter, zeroed by the caller
+  double *ovrec = nullptr;      // ovcap records
+  uint32_t *ovtile = nullptr;   // ovcap tile indices
+};
+uint32_t tile_list_capacity(const AssignGeom &g, size_t n, int scheme, bool interlace);
+int launch_tile_fill_onepass(const double *p, size_t n, const AssignGeom &g, int scheme, bool interlace,
+    uint32_t *cnt, double *lists, const TileOnePass &t, double *partials, double *wmax_part, double *wmax,
+    cudaStream_t st);
+int launch_tile_overflow(const double *ovrec, const uint32_t *ovtile, uint32_t n, const AssignGeom &g, int scheme,
+    int precision, double wscale, void *mesh0, void *mesh1, cudaStream_t st);
 int launch_unpad_copy(const void *mesh, void *dst, int ng, int rowlen,
     int precision, cudaStream_t st);
 int launch_owner_keys(const double *p, size_t n, const AssignGeom &g, int nranks,
