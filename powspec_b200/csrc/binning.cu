@@ -142,6 +142,12 @@ __global__ void __launch_bounds__(256) k_spectrum(BinGeom g, const void *__restr
       const bool self_j = (j == 0) || (((g.ng & 1) == 0) && j == (g.ng >> 1));
       if (g.symx && !self_i) wsym *= 2.0;
       if (g.symy && !self_j) wsym *= 2.0;
+      // equal box sides and no line-of-sight component along x or y: (i, j) and (j, i) have
+      // the same k^2, |k| and mu — only j <= i is visited
+      if (g.symxy && g.j0 == 0 && g.nj == g.ng) {
+        if (j > i) continue;
+        if (j < i) wsym *= 2.0;
+      }
     }
     const double ki = __ldg(g.kax[0] + i), kj = __ldg(g.kax[1] + j);
     const double k2ij = __dadd_rn(__ldg(g.kax2[0] + i), __ldg(g.kax2[1] + j));

@@ -1027,6 +1027,7 @@ int prepare_bins(psb_context *c, const psb_params *par) {
   bg.j0 = 0; bg.nj = ng;
   bg.symx = c->opt_geom_sym && (!issim || par->los[0] == 0.0);
   bg.symy = c->opt_geom_sym && (!issim || par->los[1] == 0.0);
+  bg.symxy = bg.symx && bg.symy && c->bsize[0] == c->bsize[1];
   for (int a = 0; a < 3; a++) {
     bg.los[a] = issim ? par->los[a] : 0.0;
     const double *base = c->tables.as<double>();

@@ -104,6 +104,7 @@ struct BinGeom {
   int j0, nj;           // local range of the middle (y) index of the k-space array:
                         // element (i, j0+jl, k) lives at ((i*nj + jl)*ngk + k)
   int symx, symy;       // mode counting may fold n_x / n_y (los component is zero)
+  int symxy;            // ... and swap them (both folded, equal box sides)
   double los[3];
   double k0;            // kedge[0]
   double k1;            // kedge[nbin]
