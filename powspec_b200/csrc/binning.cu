@@ -24,6 +24,8 @@
 #include "psb_internal.h"
 #include "psb_ylm.cuh"
 
+#include <algorithm>
+
 namespace psb {
 
 namespace {
@@ -320,6 +322,10 @@ int shape_for(K kernel, int nacc, int nbin, LaunchShape &ls) {
 }
 
 constexpr int MAX_BLOCKS = 148 * 8;
+// blocks per SM of the mode-counting pass (0: what fits; 1 measured best: list stage 5.21 vs
+// 5.35 ms); it runs beside the tile-list
+// pass on a side stream and competes with it for the SMs' registers (option "geom_blocks")
+int g_geom_blocks = 1;
 
 template <typename real, int NV, int MODE, bool IL, bool EVEN = false>
 int run_spectrum(const BinGeom &g, const void *Fa0, const void *Fa1, const void *Fb0,
@@ -332,6 +338,12 @@ int run_spectrum(const BinGeom &g, const void *Fa0, const void *Fa1, const void 
   size_t rows = (size_t) ((MODE == MODE_GEOM && g.symx) ? half : g.ng)
       * ((MODE == MODE_GEOM && g.symy) ? half : g.nj);
   size_t need_blocks = (rows + ls.threads / 32 - 1) / (ls.threads / 32);
+  if (MODE == MODE_GEOM && g_geom_blocks > 0) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    ls.blocks = std::min(ls.blocks, sms * g_geom_blocks);
+  }
   if ((size_t) ls.blocks > need_blocks) ls.blocks = (int) need_blocks;
   if (ls.blocks > MAX_BLOCKS) ls.blocks = MAX_BLOCKS;
   if ((size_t) ls.blocks * nacc * sizeof(double) > scratch_bytes) {
@@ -346,6 +358,8 @@ int run_spectrum(const BinGeom &g, const void *Fa0, const void *Fa1, const void 
 }
 
 }  // namespace
+
+void bin_set_geom_blocks(int n) { g_geom_blocks = n; }
 
 size_t bin_scratch_bytes(const BinGeom &g) {
   // block partials plus one accumulator row for the geometry pass
