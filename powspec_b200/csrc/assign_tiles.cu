@@ -128,6 +128,7 @@ __device__ __forceinline__ TileSet tile_set(double2 a, double2 b, const AssignGe
 // goes to a global overflow list of (record, tile) that a small kernel adds to the mesh
 // after the tiles have been stored.
 struct OnePass {
+  int index = 0;                // lists hold 4-byte particle indices instead of the 32-byte records
   uint32_t cap = 0;             // slots per tile; 0: exact lists (count + scan + fill)
   uint32_t ovcap = 0;
   uint32_t *ovcount = nullptr;
@@ -136,9 +137,13 @@ struct OnePass {
 };
 
 __device__ __forceinline__ void put_entry(const OnePass &op, double2 *__restrict__ out, uint32_t tile, uint32_t pos,
-    double2 a, double2 b) {
-  if (op.cap == 0u) { st_record(out, pos, a, b); return; }
-  if (pos < op.cap) { st_record(out, (size_t) tile * op.cap + pos, a, b); return; }
+    double2 a, double2 b, uint32_t index) {
+  if (op.cap == 0u || pos < op.cap) {
+    const size_t slot = op.cap ? (size_t) tile * op.cap + pos : (size_t) pos;
+    if (op.index) reinterpret_cast<uint32_t *>(out)[slot] = index;
+    else st_record(out, slot, a, b);
+    return;
+  }
   const uint32_t q = atomicAdd(op.ovcount, 1u);
   if (q < op.ovcap) { st_record(op.ovrec, q, a, b); op.ovtile[q] = tile; }
 }
@@ -146,14 +151,14 @@ __device__ __forceinline__ void put_entry(const OnePass &op, double2 *__restrict
 // the up to seven further tiles of a particle that straddles tile faces
 template <bool FILL>
 __device__ __forceinline__ void tile_extra(const TileSet &ts, uint32_t *__restrict__ cnt_or_cursor,
-    double2 *__restrict__ out, double2 a, double2 b, const OnePass &op) {
+    double2 *__restrict__ out, double2 a, double2 b, const OnePass &op, uint32_t index) {
 #pragma unroll
   for (int m = 1; m < 8; m++) {
     if (((m & 1) && !ts.step[2]) || ((m & 2) && !ts.step[1]) || ((m & 4) && !ts.step[0])) continue;
     const uint32_t tile = ts.first + ((m & 1) ? ts.step[2] : 0u) + ((m & 2) ? ts.step[1] : 0u) +
         ((m & 4) ? ts.step[0] : 0u);
     const uint32_t pos = atomicAdd(cnt_or_cursor + tile, 1u);
-    if (FILL) put_entry(op, out, tile, pos, a, b);
+    if (FILL) put_entry(op, out, tile, pos, a, b, index);
   }
 }
 
@@ -196,12 +201,12 @@ __global__ void __launch_bounds__(256) k_tile_lists(const double2 *__restrict__ 
     if (FILL) {
 #pragma unroll
       for (int u = 0; u < UNROLL; u++)
-        if (i0 + u * stride < n) put_entry(op, out, ts[u].first, pos[u], a[u], b[u]);
+        if (i0 + u * stride < n) put_entry(op, out, ts[u].first, pos[u], a[u], b[u], (uint32_t) (i0 + u * stride));
     }
     if (more) {
 #pragma unroll
       for (int u = 0; u < UNROLL; u++)
-        if (i0 + u * stride < n) tile_extra<FILL>(ts[u], cnt_or_cursor, out, a[u], b[u], op);
+        if (i0 + u * stride < n) tile_extra<FILL>(ts[u], cnt_or_cursor, out, a[u], b[u], op, (uint32_t) (i0 + u * stride));
     }
   }
   if (!STATS) return;
@@ -378,7 +383,8 @@ struct TileMaps { CUtensorMap m[2]; };
 template <int SCHEME, typename real, int NFIELD, int MODE, bool TMA>
 __global__ void __launch_bounds__(ACC_THREADS, ACC_BLOCKS) k_tile_accumulate(const double2 *__restrict__ parts,
     const uint32_t *__restrict__ start, AssignGeom g, double wscale, const double *__restrict__ wmax_dev,
-    real *__restrict__ mesh0, real *__restrict__ mesh1, const __grid_constant__ TileMaps maps, uint32_t cap) {
+    real *__restrict__ mesh0, real *__restrict__ mesh1, const __grid_constant__ TileMaps maps, uint32_t cap,
+    const uint32_t *__restrict__ ilist) {
   extern __shared__ __align__(1024) uint32_t sm[];      // cell c: words 2c, 2c + 1 = its limbs (limb_swap)
   __shared__ uint16_t queue[BATCH];             // listed particles (index in the batch) that straddle the tile's z faces
   __shared__ uint32_t nqueue;
@@ -409,12 +415,12 @@ __global__ void __launch_bounds__(ACC_THREADS, ACC_BLOCKS) k_tile_accumulate(con
       for (uint32_t base = 0; base < np; base += BATCH) {
         const uint32_t lim = min(np, base + BATCH);
         for (uint32_t j = base + threadIdx.x; j < lim; j += ACC_THREADS)
-          if (tile_add<SCHEME, false>(parts, lbase + j, f, g, wnorm, x0, y0, z0, sm_lo))
+          if (tile_add<SCHEME, false>(parts, ilist ? (size_t) __ldg(ilist + lbase + j) : lbase + j, f, g, wnorm, x0, y0, z0, sm_lo))
             queue[atomicAdd(&nqueue, 1u)] = (uint16_t) (j - base);
         __syncthreads();
         const uint32_t nq = nqueue;
         for (uint32_t k = threadIdx.x; k < nq; k += ACC_THREADS)
-          tile_add<SCHEME, true>(parts, lbase + base + queue[k], f, g, wnorm, x0, y0, z0, sm_lo);
+          tile_add<SCHEME, true>(parts, ilist ? (size_t) __ldg(ilist + lbase + base + queue[k]) : lbase + base + queue[k], f, g, wnorm, x0, y0, z0, sm_lo);
         __syncthreads();
         if (threadIdx.x == 0) nqueue = 0;
         if (lim < np) {
@@ -602,7 +608,7 @@ int g_tile_tma = 1;     // ablation switch (psb_set_option "tile_tma")
 
 template <int SCHEME, typename real>
 int launch_accumulate(const double *parts, const uint32_t *start, const AssignGeom &g, double wscale,
-    const double *wmax, bool add, void *m0, void *m1, uint32_t cap, cudaStream_t st) {
+    const double *wmax, bool add, void *m0, void *m1, uint32_t cap, const uint32_t *ilist, cudaStream_t st) {
   const size_t smem = (size_t) TCELLS * 8;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -618,7 +624,7 @@ int launch_accumulate(const double *parts, const uint32_t *start, const AssignGe
   do {                                                                                            \
     auto kern = k_tile_accumulate<SCHEME, real, NF, MODE, TMA>;                                   \
     PSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
-    kern<<<ACC_BLOCKS * sms, ACC_THREADS, smem, st>>>(pp, start, g, wscale, wmax, a, b, maps, cap);              \
+    kern<<<ACC_BLOCKS * sms, ACC_THREADS, smem, st>>>(pp, start, g, wscale, wmax, a, b, maps, cap, ilist);              \
   } while (0)
   if constexpr (sizeof(real) == 8) {
     if (tma) { if (m1) PSB_ACC(2, 0, true); else PSB_ACC(1, 0, true); }
@@ -686,11 +692,14 @@ int launch_tile_count(const double *p, size_t n, const AssignGeom &g, int scheme
 
 // cursor: the exclusive scan of the counts (consumed); lists: records, grouped by tile
 int launch_tile_fill(const double *p, size_t n, const AssignGeom &g, int scheme, bool interlace,
-    uint32_t *cursor, double *lists, cudaStream_t st) {
+    uint32_t *cursor, void *lists, bool index, cudaStream_t st) {
+  OnePass op;
+  op.index = index;
+  double *out = static_cast<double *>(lists);
 #define PSB_LISTS(S)                                                                              \
   case S:                                                                                         \
-    return interlace ? launch_lists<S, true>(p, n, g, 1, cursor, lists, nullptr, nullptr, OnePass{}, st)  \
-                     : launch_lists<S, false>(p, n, g, 1, cursor, lists, nullptr, nullptr, OnePass{}, st);
+    return interlace ? launch_lists<S, true>(p, n, g, 1, cursor, out, nullptr, nullptr, op, st)  \
+                     : launch_lists<S, false>(p, n, g, 1, cursor, out, nullptr, nullptr, op, st);
   switch (scheme) { PSB_LISTS(0) PSB_LISTS(1) PSB_LISTS(2) PSB_LISTS(3) default: return -1; }
 #undef PSB_LISTS
 }
@@ -700,9 +709,11 @@ int launch_tile_fill(const double *p, size_t n, const AssignGeom &g, int scheme,
 // *op.ovcount (zeroed by the caller) counts the entries that did not fit.  Also reduces the
 // coordinate bounds (optional) and max |w| like launch_tile_count.
 int launch_tile_fill_onepass(const double *p, size_t n, const AssignGeom &g, int scheme, bool interlace,
-    uint32_t *cnt, double *lists, const TileOnePass &t, double *partials, double *wmax_part, double *wmax,
+    uint32_t *cnt, void *lists_, const TileOnePass &t, double *partials, double *wmax_part, double *wmax,
     cudaStream_t st) {
   OnePass op;
+  double *lists = static_cast<double *>(lists_);
+  op.index = t.index;
   op.cap = t.cap; op.ovcap = t.ovcap; op.ovcount = t.ovcount;
   op.ovrec = reinterpret_cast<double2 *>(t.ovrec); op.ovtile = t.ovtile;
 #define PSB_LISTS(S)                                                                              \
@@ -739,12 +750,12 @@ int launch_tile_overflow(const double *ovrec, const uint32_t *ovtile, uint32_t n
 // start: tile_list_count + 1 offsets into lists; add: the meshes already hold data
 int launch_tile_accumulate(const double *lists, const uint32_t *start, const AssignGeom &g, int scheme,
     int precision, double wscale, const double *wmax, bool add, void *mesh0, void *mesh1, cudaStream_t st,
-    uint32_t cap) {
+    uint32_t cap, const uint32_t *ilist) {
 #define PSB_DISPATCH(S)                                                                           \
   case S:                                                                                         \
     return precision == 8                                                                         \
-        ? launch_accumulate<S, double>(lists, start, g, wscale, wmax, add, mesh0, mesh1, cap, st) \
-        : launch_accumulate<S, float>(lists, start, g, wscale, wmax, add, mesh0, mesh1, cap, st);
+        ? launch_accumulate<S, double>(lists, start, g, wscale, wmax, add, mesh0, mesh1, cap, ilist, st) \
+        : launch_accumulate<S, float>(lists, start, g, wscale, wmax, add, mesh0, mesh1, cap, ilist, st);
   switch (scheme) {
     PSB_DISPATCH(0) PSB_DISPATCH(1) PSB_DISPATCH(2) PSB_DISPATCH(3)
     default: set_error("unrecognised particle assignment scheme: %d\n", scheme); return -1;

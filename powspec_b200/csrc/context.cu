@@ -301,7 +301,7 @@ int zero_if_fresh(psb_context *c, const AssignGeom &g, int precision, void *m0, 
 // count + scan + fill, and the next 16 dense chunks go there directly.  Uniform catalogues:
 // list stage 6.27 -> 5.73 ms.
 int tile_lists_exact(psb_context *c, const double *src, size_t len, const AssignGeom &g, int scheme,
-    bool interlace, double *partials, double *wmax, size_t ntile) {
+    bool interlace, double *partials, double *wmax, size_t ntile, bool index) {
   size_t tmp_bytes = c->tile_scan_bytes;
   uint32_t total = 0;
   PSB_CUDA(cudaMemsetAsync(c->tile_cnt.p, 0, (ntile + 1) * 4, c->st));
@@ -312,9 +312,9 @@ int tile_lists_exact(psb_context *c, const double *src, size_t len, const Assign
   // the list buffer is sized from the total: one small host wait per chunk
   PSB_CUDA(cudaMemcpyAsync(&total, c->tile_start.as<uint32_t>() + ntile, 4, cudaMemcpyDeviceToHost, c->st));
   PSB_CUDA(cudaStreamSynchronize(c->st));
-  if (c->sorted.reserve((size_t) (total ? total : 1) * 32)) return -1;
+  if (c->sorted.reserve((size_t) (total ? total : 1) * (index ? 4 : 32))) return -1;
   PSB_CUDA(cudaMemcpyAsync(c->tile_cnt.p, c->tile_start.p, (ntile + 1) * 4, cudaMemcpyDeviceToDevice, c->st));
-  if (launch_tile_fill(src, len, g, scheme, interlace, c->tile_cnt.as<uint32_t>(), c->sorted.as<double>(), c->st))
+  if (launch_tile_fill(src, len, g, scheme, interlace, c->tile_cnt.as<uint32_t>(), c->sorted.p, index, c->st))
     return -1;
   c->launches += 6;
   return 0;
@@ -337,7 +337,14 @@ int tile_assign_chunk(psb_context *c, const double *src, size_t len, const Assig
   double *wmax = c->wmax_buf.as<double>();
   // one-pass lists: capacity per tile, overflow room for 1/64 of the particles
   uint32_t cap = c->opt_tile_cap > 0 ? (uint32_t) c->opt_tile_cap : tile_list_capacity(g, len, scheme, interlace);
-  const size_t list_bytes = ntile * (size_t) cap * 32;
+  // Index lists (option tile_index, off): the scattered 32-byte record stores of the fill pass
+  // run at 1.4 TB/s — every store opens another DRAM row (tools/fill_probe.cu: 3.3 ms for the
+  // stores alone, 1.3 ms for the returning atomics alone) — while 4-byte indices merge in the
+  // L2.  But then the accumulation has to gather the records, one random DRAM sector each,
+  // behind a dependent load: measured list stage 5.6 -> 5.1 ms, accumulation 10.7 -> 15.4 ms.
+  // The copies stay: the random access is paid once, as a store, where nothing waits for it.
+  const bool index = c->opt_tile_index != 0;
+  const size_t list_bytes = ntile * (size_t) cap * (index ? 4 : 32);
   bool onepass = c->opt_tile_onepass != 0 && c->tile_onepass_backoff == 0 && list_bytes <= ((size_t) 24 << 30);
   if (c->tile_onepass_backoff > 0) c->tile_onepass_backoff--;
   uint32_t nover = 0;
@@ -346,6 +353,7 @@ int tile_assign_chunk(psb_context *c, const double *src, size_t len, const Assig
     StageScope sc(c, PSB_T_SORT, c->st);
     if (onepass) {
       op.cap = cap;
+      op.index = index;
       op.ovcap = c->opt_tile_ovcap > 0 ? (uint32_t) c->opt_tile_ovcap : (uint32_t) std::max<size_t>(4096, len / 64);
       if (c->sorted.reserve(list_bytes) || c->tile_ovrec.reserve((size_t) op.ovcap * 32) ||
           c->tile_ovtile.reserve((size_t) op.ovcap * 4 + 16))
@@ -355,7 +363,7 @@ int tile_assign_chunk(psb_context *c, const double *src, size_t len, const Assig
       op.ovcount = op.ovtile + op.ovcap;        // the counter lives behind the tile indices
       PSB_CUDA(cudaMemsetAsync(c->tile_cnt.p, 0, (ntile + 1) * 4, c->st));
       PSB_CUDA(cudaMemsetAsync(op.ovcount, 0, 4, c->st));
-      if (launch_tile_fill_onepass(src, len, g, scheme, interlace, c->tile_cnt.as<uint32_t>(), c->sorted.as<double>(),
+      if (launch_tile_fill_onepass(src, len, g, scheme, interlace, c->tile_cnt.as<uint32_t>(), c->sorted.p,
             op, partials, wmax + 1, wmax, c->st))
         return -1;
       c->launches += 3;
@@ -367,17 +375,20 @@ int tile_assign_chunk(psb_context *c, const double *src, size_t len, const Assig
         c->tile_onepass_backoff = 16;
       }
     }
-    if (!onepass && tile_lists_exact(c, src, len, g, scheme, interlace, partials, wmax, ntile)) return -1;
+    if (!onepass && tile_lists_exact(c, src, len, g, scheme, interlace, partials, wmax, ntile, index)) return -1;
   }
-  if (consumed) PSB_CUDA(cudaEventRecord(consumed, c->st));
+  // with index lists the accumulation still reads the source records
+  if (consumed && !index) PSB_CUDA(cudaEventRecord(consumed, c->st));
   if (c->memset_pending) { PSB_CUDA(cudaStreamWaitEvent(c->st, c->memset_pending, 0)); c->memset_pending = nullptr; }
   const bool add = !(fresh && *fresh);
   if (fresh) *fresh = false;
   StageScope sc(c, PSB_T_ASSIGN, c->st);
-  if (launch_tile_accumulate(c->sorted.as<double>(), onepass ? c->tile_cnt.as<uint32_t>() : c->tile_start.as<uint32_t>(),
-        g, scheme, precision, wscale, wmax, add, m0, m1, c->st, onepass ? cap : 0))
+  if (launch_tile_accumulate(index ? src : c->sorted.as<double>(),
+        onepass ? c->tile_cnt.as<uint32_t>() : c->tile_start.as<uint32_t>(), g, scheme, precision, wscale, wmax, add,
+        m0, m1, c->st, onepass ? cap : 0, index ? c->sorted.as<uint32_t>() : nullptr))
     return -1;
   c->launches++;
+  if (consumed && index) PSB_CUDA(cudaEventRecord(consumed, c->st));
   if (onepass && nover) {
     if (launch_tile_overflow(op.ovrec, op.ovtile, nover, g, scheme, precision, wscale, m0, m1, c->st)) return -1;
     c->launches++;
@@ -1188,6 +1199,7 @@ int psb_set_option(psb_context *c, const char *name, long value) {
   if (!strcmp(name, "geom_blocks")) { bin_set_geom_blocks((int) value); return 0; }
   if (!strcmp(name, "tile_onepass")) { c->opt_tile_onepass = value; c->tile_onepass_backoff = 0; return 0; }
   if (!strcmp(name, "tile_cap")) { c->opt_tile_cap = value; return 0; }
+  if (!strcmp(name, "tile_index")) { c->opt_tile_index = value; return 0; }
   if (!strcmp(name, "tile_ovcap")) { c->opt_tile_ovcap = value; return 0; }
   if (!strcmp(name, "tile_tma")) { tile_set_tma((int) value); return 0; }
   if (!strcmp(name, "l2_fetch")) {          // L2 fetch granularity hint in bytes (32 / 64 / 128)

@@ -120,6 +120,7 @@ struct psb_context {
   long opt_sort_min = 1 << 16;
   long opt_geom_sym = 1;                // fold +-n_x, +-n_y in the mode-counting pass
   long opt_tile_onepass = 1;            // tile lists in one pass (fixed capacity + overflow list)
+  long opt_tile_index = 0;              // 1: tile lists of 4-byte particle indices instead of record copies (ablation: slower)
   long opt_tile_cap = 0;                // > 0: slots per tile (tests: forces overflow)
   long opt_tile_ovcap = 0;              // > 0: room of the overflow list (tests: forces the fallback)
   long opt_owner = -1;                  // owner-computes tile assignment: 1 / 0 / -1 = when the chunk is dense

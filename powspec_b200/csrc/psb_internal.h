@@ -66,14 +66,17 @@ void tile_set_tma(int on);      // 0: flush tiles with thread stores instead of 
 size_t tile_list_count(const AssignGeom &g);
 int launch_tile_count(const double *p, size_t n, const AssignGeom &g, int scheme, bool interlace,
     uint32_t *cnt, double *partials, double *wmax_part, double *wmax, cudaStream_t st);
+// index: the lists hold 4-byte particle indices (into p) instead of copies of the records
 int launch_tile_fill(const double *p, size_t n, const AssignGeom &g, int scheme, bool interlace,
-    uint32_t *cursor, double *lists, cudaStream_t st);
-// cap > 0: one-pass lists (cap slots per tile, start[] holds the list lengths)
+    uint32_t *cursor, void *lists, bool index, cudaStream_t st);
+// cap > 0: one-pass lists (cap slots per tile, start[] holds the list lengths); ilist: index
+// lists (then `lists` is the particle array they point into)
 int launch_tile_accumulate(const double *lists, const uint32_t *start, const AssignGeom &g, int scheme,
     int precision, double wscale, const double *wmax, bool add, void *mesh0, void *mesh1, cudaStream_t st,
-    uint32_t cap = 0);
+    uint32_t cap = 0, const uint32_t *ilist = nullptr);
 // one-pass lists: fixed capacity per tile, overflow list (assign_tiles.cu)
 struct TileOnePass {
+  int index = 0;                // index lists
   uint32_t cap = 0, ovcap = 0;
   uint32_t *ovcount = nullptr;  // device counter, zeroed by the caller
   double *ovrec = nullptr;      // ovcap records
@@ -81,7 +84,7 @@ struct TileOnePass {
 };
 uint32_t tile_list_capacity(const AssignGeom &g, size_t n, int scheme, bool interlace);
 int launch_tile_fill_onepass(const double *p, size_t n, const AssignGeom &g, int scheme, bool interlace,
-    uint32_t *cnt, double *lists, const TileOnePass &t, double *partials, double *wmax_part, double *wmax,
+    uint32_t *cnt, void *lists, const TileOnePass &t, double *partials, double *wmax_part, double *wmax,
     cudaStream_t st);
 int launch_tile_overflow(const double *ovrec, const uint32_t *ovtile, uint32_t n, const AssignGeom &g, int scheme,
     int precision, double wscale, void *mesh0, void *mesh1, cudaStream_t st);
