@@ -176,8 +176,10 @@ long psb_tile_overflow(const psb_context *ctx);
 
 /* Tunables (tests / ablations; the list is in psb_set_option, csrc/context.cu):
  * "sort", "strip", "coop", "owner", "own_fft", "fft_fused", "stream", "stream_chunk",
- * "stream_taper", "h2d_threads", "survey_direct", "geom_sym" ...; returns non-zero
- * for an unknown name */
+ * "stream_taper", "h2d_threads", "survey_direct", "geom_sym", and for the owner-computes
+ * assignment "tile_onepass", "tile_cap", "tile_ovcap", "tile_index", "tile_tma",
+ * "tile_fill_unroll", for the FFT passes "fft_skip", "fft_store_skip", "fft_variant",
+ * "geom_blocks" ...; returns non-zero for an unknown name */
 int psb_set_option(psb_context *ctx, const char *name, long value);
 
 const char *psb_last_error(void);
