@@ -499,7 +499,8 @@ __global__ void __launch_bounds__(ACC_THREADS, ACC_BLOCKS) k_tile_accumulate(con
   }
 }
 
-int g_fill_unroll = 4;  // particles in flight per thread of the fill pass (psb_set_option "tile_fill_unroll")
+int g_fill_unroll = 2;  // particles in flight per thread of the fill pass (psb_set_option "tile_fill_unroll"): the
+                        // one-pass fill with 4 needs 100 registers (2 blocks per SM): list stage 5.6 vs 4.6 ms with 2 or 1
 
 // One-pass lists: the entries that did not fit their tile's slots.  One thread per
 // (particle, tile) entry adds the in-tile part of the particle's stencils to the mesh with
@@ -562,8 +563,11 @@ int launch_lists(const double *p, size_t n, const AssignGeom &g, int mode, uint3
   const double2 *pp = reinterpret_cast<const double2 *>(p);
   const int nblk = row_keys_blocks(n);
   double2 *o = reinterpret_cast<double2 *>(out);
-  if (mode == 2)
-    k_tile_lists<SCHEME, INTERLACE, true, 4, true><<<nblk, 256, 0, st>>>(pp, n, g, cnt, o, partials, wmax_part, op);
+  if (mode == 2) {
+    if (g_fill_unroll >= 4) k_tile_lists<SCHEME, INTERLACE, true, 4, true><<<nblk, 256, 0, st>>>(pp, n, g, cnt, o, partials, wmax_part, op);
+    else if (g_fill_unroll >= 2) k_tile_lists<SCHEME, INTERLACE, true, 2, true><<<nblk, 256, 0, st>>>(pp, n, g, cnt, o, partials, wmax_part, op);
+    else k_tile_lists<SCHEME, INTERLACE, true, 1, true><<<nblk, 256, 0, st>>>(pp, n, g, cnt, o, partials, wmax_part, op);
+  }
   else if (mode == 1) {
     if (g_fill_unroll >= 4) k_tile_lists<SCHEME, INTERLACE, true, 4, false><<<nblk, 256, 0, st>>>(pp, n, g, cnt, o, nullptr, nullptr, op);
     else if (g_fill_unroll >= 2) k_tile_lists<SCHEME, INTERLACE, true, 2, false><<<nblk, 256, 0, st>>>(pp, n, g, cnt, o, nullptr, nullptr, op);
