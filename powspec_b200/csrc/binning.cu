@@ -291,12 +291,14 @@ __global__ void k_unpack_geometry(const double *__restrict__ acc, int nbin, int 
   for (int l = 0; l < nl; l++) lcnt[l * nbin + b] = acc[(2 + l) * nbin + b];
 }
 
+int g_bin_threads = 256;        // block size of the binning kernels (option "bin_threads")
+
 struct LaunchShape { int blocks, threads; size_t smem; };
 
 template <typename K>
 int shape_for(K kernel, int nacc, int nbin, LaunchShape &ls) {
   // bin thresholds + warp-private bins (nacc doubles per warp)
-  int threads = 256;
+  int threads = g_bin_threads;
   auto bytes = [&](int t) { return ((size_t) nacc * (t / 32) + nbin + 1) * sizeof(double); };
   size_t smem = bytes(threads);
   while (smem > 200 * 1024 && threads > 32) {
@@ -360,6 +362,7 @@ int run_spectrum(const BinGeom &g, const void *Fa0, const void *Fa1, const void 
 }  // namespace
 
 void bin_set_geom_blocks(int n) { g_geom_blocks = n; }
+void bin_set_threads(int n) { g_bin_threads = (n == 64 || n == 128 || n == 256) ? n : 256; }
 
 size_t bin_scratch_bytes(const BinGeom &g) {
   // block partials plus one accumulator row for the geometry pass

@@ -1196,6 +1196,7 @@ int psb_set_option(psb_context *c, const char *name, long value) {
   if (!strcmp(name, "fft_variant")) { fft_set_variant((int) value); return 0; }
   if (!strcmp(name, "fft_store_skip")) { c->opt_fft_store_skip = value; return 0; }
   if (!strcmp(name, "tile_fill_unroll")) { tile_set_fill_unroll((int) value); return 0; }
+  if (!strcmp(name, "bin_threads")) { bin_set_threads((int) value); return 0; }
   if (!strcmp(name, "geom_blocks")) { bin_set_geom_blocks((int) value); return 0; }
   if (!strcmp(name, "tile_onepass")) { c->opt_tile_onepass = value; c->tile_onepass_backoff = 0; return 0; }
   if (!strcmp(name, "tile_cap")) { c->opt_tile_cap = value; return 0; }

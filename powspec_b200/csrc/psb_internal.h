@@ -139,6 +139,7 @@ int launch_bin(const BinGeom &g, int precision, const void *Fa0, const void *Fa1
     size_t scratch_bytes, cudaStream_t st);
 size_t bin_scratch_bytes(const BinGeom &g);
 void bin_set_geom_blocks(int n);
+void bin_set_threads(int n);
 // in-place interlace combination F0 <- (F0 + phase F1)/2 (survey l>0 needs the field)
 int launch_combine(const BinGeom &g, int precision, void *F0, const void *F1,
     cudaStream_t st);
