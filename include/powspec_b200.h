@@ -176,7 +176,7 @@ long psb_tile_overflow(const psb_context *ctx);
 
 /* Tunables (tests / ablations; the list is in psb_set_option, csrc/context.cu):
  * "sort", "strip", "coop", "owner", "own_fft", "fft_fused", "stream", "stream_chunk",
- * "stream_taper", "h2d_threads", "survey_direct", "geom_sym", and for the owner-computes
+ * "stream_taper", "h2d_threads", "h2d_nt" (0: plain memcpy in the staging pool), "survey_direct", "geom_sym", and for the owner-computes
  * assignment "tile_onepass", "tile_cap", "tile_ovcap", "tile_index", "tile_tma",
  * "tile_fill_unroll", for the FFT passes "fft_skip", "fft_store_skip", "fft_variant",
  * "geom_blocks" ...; returns non-zero for an unknown name */
@@ -322,6 +322,14 @@ int psb_generate_into(psb_context *ctx, double *dst_dev, size_t n, double boxsiz
 void psb_device_free(psb_context *ctx, void *ptr);
 /* copy device catalogue to host (tests) */
 int psb_copy_to_host(psb_context *ctx, void *dst, const void *src_dev, size_t bytes);
+/* test hook, no GPU needed: the staging copy that carries pageable host catalogues (the
+ * reference's malloc'd DATA arrays, src/read_cata.c:86-189) into the pinned upload buffers —
+ * a persistent pool of `nthreads` host threads with non-temporal stores (csrc/hostcopy.cpp).
+ * Copies src to dst `repeats` times; returns the number of threads the pool was asked for */
+int psb_test_host_copy(void *dst, const void *src, size_t bytes, int nthreads, int repeats);
+/* the same, as the upload path uses it: `bytes` of src streamed through two alternating staging
+ * buffers of `piece` bytes by ONE pool; returns the seconds taken (tools/staging_bench.py) */
+double psb_test_host_stage(const void *src, size_t bytes, size_t piece, int nthreads, int stream_stores);
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,7 @@ ROOT = os.path.dirname(HERE)
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libpowspec_b200.so")
 
-SOURCES = ["assign.cu", "assign_tiles.cu", "binning.cu", "fft_strided.cu", "cnvt.cu", "ingest.cu", "generate.cu", "context.cu", "dist.cu", "refabi.cpp"]
+SOURCES = ["assign.cu", "assign_tiles.cu", "binning.cu", "fft_strided.cu", "cnvt.cu", "ingest.cu", "generate.cu", "context.cu", "dist.cu", "hostcopy.cpp", "refabi.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -528,6 +528,12 @@ int h2d_async(psb_context *c, void *dst, const void *src, size_t bytes, bool pin
   }
   unsigned hw = std::thread::hardware_concurrency();
   const int nthr = (int) std::max(1u, std::min((unsigned) std::max<long>(c->opt_h2d_threads, 1), hw ? hw : 1u));
+  // the staging threads live as long as the context (round 1 created and joined them for
+  // every 64 MB piece); the copy streams past the caches (hostcopy.cpp)
+  if (!c->copy_pool || copy_pool_threads(c->copy_pool) != nthr) {
+    copy_pool_destroy(c->copy_pool);
+    c->copy_pool = copy_pool_create(nthr);
+  }
   size_t off = 0;
   int slot = 0;
   while (off < bytes) {
@@ -535,16 +541,7 @@ int h2d_async(psb_context *c, void *dst, const void *src, size_t bytes, bool pin
     PSB_CUDA(cudaEventSynchronize(c->pinned_free[slot]));
     char *stage = static_cast<char *>(c->pinned[slot]);
     const char *from = static_cast<const char *>(src) + off;
-    if (nthr == 1 || len < ((size_t) 4 << 20)) memcpy(stage, from, len);
-    else {
-      std::vector<std::thread> th;
-      const size_t per = (len / nthr + 4095) & ~(size_t) 4095;
-      for (int t = 0; t < nthr; t++) {
-        const size_t a = std::min(len, per * t), b = std::min(len, per * (t + 1));
-        if (b > a) th.emplace_back([=] { memcpy(stage + a, from + a, b - a); });
-      }
-      for (auto &t : th) t.join();
-    }
+    copy_pool_run(c->copy_pool, stage, from, len);
     PSB_CUDA(cudaMemcpyAsync(static_cast<char *>(dst) + off, stage, len,
         cudaMemcpyHostToDevice, stream));
     PSB_CUDA(cudaEventRecord(c->pinned_free[slot], stream));
@@ -1160,6 +1157,8 @@ void psb_destroy(psb_context *c) {
     if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]);
   }
   if (c->st_copy) cudaStreamDestroy(c->st_copy);
+  copy_pool_destroy(c->copy_pool);
+  c->copy_pool = nullptr;
   c->fka.release(); c->sorted.release(); c->keys.release(); c->hist.release();
   c->tile_cnt.release(); c->tile_start.release(); c->wmax_buf.release();
   c->tile_ovrec.release(); c->tile_ovtile.release();
@@ -1216,6 +1215,7 @@ int psb_set_option(psb_context *c, const char *name, long value) {
   if (!strcmp(name, "geom_sym")) { c->opt_geom_sym = value; return 0; }
   if (!strcmp(name, "stream")) { c->opt_stream = value; return 0; }
   if (!strcmp(name, "h2d_threads")) { c->opt_h2d_threads = value; return 0; }
+  if (!strcmp(name, "h2d_nt")) { copy_set_stream_stores((int) value); return 0; }
   if (!strcmp(name, "stream_chunk")) { c->opt_stream_chunk = value; return 0; }
   if (!strcmp(name, "stream_taper")) { c->opt_stream_taper = value; return 0; }
   set_error("unknown option: %s\n", name);

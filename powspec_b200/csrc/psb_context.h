@@ -62,6 +62,16 @@ using psb::Interval;
 using psb::AssignGeom;
 using psb::BinGeom;
 
+// staging copy pageable -> pinned memory by a persistent thread pool (hostcopy.cpp)
+namespace psb_host {
+struct CopyPool;
+CopyPool *copy_pool_create(int nthreads);
+void copy_pool_destroy(CopyPool *p);
+int copy_pool_threads(const CopyPool *p);
+void copy_pool_run(CopyPool *p, void *dst, const void *src, size_t bytes);
+void copy_set_stream_stores(int on);
+}  // namespace psb_host
+
 // ---------------------------------------------------------------------------
 // the context
 // ---------------------------------------------------------------------------
@@ -91,6 +101,7 @@ struct psb_context {
   void *pinned[2] = {nullptr, nullptr};
   size_t pinned_bytes = 0;
   cudaEvent_t pinned_free[2] = {nullptr, nullptr};
+  psb_host::CopyPool *copy_pool = nullptr;      // persistent staging threads (hostcopy.cpp)
 
   // meshes: [cat][field]; survey extras
   DevBuf mesh[2][2];
@@ -141,7 +152,8 @@ struct psb_context {
   long opt_strip = 64;                  // rows per strip of the sort order
   long opt_h2d_threads = 16;            // host threads staging pageable memory into pinned buffers
                                         // (capped at the hardware concurrency; 8 -> 16 on the 16-core
-                                        // B200 host: 36 -> 44 GB/s, config 2 from malloc'd memory 121 -> 107 ms)
+                                        // B200 host: 36 -> 44 GB/s, config 2 from malloc'd memory 121 -> 107 ms;
+                                        // since round 2 a persistent pool with streaming stores, hostcopy.cpp)
   long opt_stream = 1;                  // overlap H2D with assignment for host catalogues (sims)
   long opt_stream_chunk = 12500000;     // particles per streamed chunk (400 MB): the smallest whose
                                         // sort + scatter (~6 ms, one sweep of the meshes) still keeps

@@ -84,3 +84,21 @@ def test_refabi_struct_layout_matches_reference_headers(tmp_path):
                                "-I", os.path.join(ROOT, "oracle", "fftw_shim"),
                                "-I", os.path.join(ref, "src"), "-I", os.path.join(ROOT, "include"),
                                "-c", str(c), "-o", str(tmp_path / "layout.o")])
+
+
+def test_staging_copy_pool(lib):
+    """The pageable -> pinned staging copy (csrc/hostcopy.cpp): byte-exact for aligned and
+    ragged sizes / offsets, one thread and many, reused over several pieces."""
+    import numpy as np
+    lib.psb_test_host_copy.restype = C.c_int
+    lib.psb_test_host_copy.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
+    rng = np.random.default_rng(7)
+    src = rng.integers(0, 256, size=(24 << 20) + 4099, dtype=np.uint8)
+    for nthr in (1, 3, 16):
+        for off_s, off_d, n in ((0, 0, src.size), (1, 0, 5 << 20), (3, 13, (9 << 20) + 77),
+                                (0, 64, 100), (5, 7, 255), (0, 0, 0), (8, 24, 4096 * 33 + 1)):
+            dst = np.zeros(src.size + 128, dtype=np.uint8)
+            got = lib.psb_test_host_copy(dst.ctypes.data + off_d, src.ctypes.data + off_s, n, nthr, 3)
+            assert got == nthr
+            assert np.array_equal(dst[off_d:off_d + n], src[off_s:off_s + n]), (nthr, off_s, off_d, n)
+            assert not dst[:off_d].any() and not dst[off_d + n:].any(), (nthr, off_s, off_d, n)
