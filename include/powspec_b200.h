@@ -176,7 +176,7 @@ long psb_tile_overflow(const psb_context *ctx);
 
 /* Tunables (tests / ablations; the list is in psb_set_option, csrc/context.cu):
  * "sort", "strip", "coop", "owner", "own_fft", "fft_fused", "stream", "stream_chunk",
- * "stream_taper", "h2d_threads", "h2d_nt" (0: plain memcpy in the staging pool), "survey_direct", "geom_sym", and for the owner-computes
+ * "stream_taper", "h2d_threads", "h2d_nt" (0: plain memcpy in the staging pool), "h2d_wc" (1: write-combined staging buffers), "h2d_piece_mb", "h2d_slots" (the staging ring), "survey_direct", "geom_sym", and for the owner-computes
  * assignment "tile_onepass", "tile_cap", "tile_ovcap", "tile_index", "tile_tma",
  * "tile_fill_unroll", for the FFT passes "fft_skip", "fft_store_skip", "fft_variant",
  * "geom_blocks" ...; returns non-zero for an unknown name */

@@ -509,8 +509,8 @@ int bounds_finish(psb_context *c, const psb_params *par) {
 
 // Copy `bytes` from host memory into a device buffer on the copy stream.
 // Pinned sources go straight to the copy engine; pageable ones are staged
-// through two pinned buffers filled by a few host threads, so the PCIe transfer
-// is not bound by one memcpy thread.
+// through a ring of pinned buffers filled by a persistent pool of host threads
+// (hostcopy.cpp), so the PCIe transfer is not bound by one memcpy thread.
 int h2d_async(psb_context *c, void *dst, const void *src, size_t bytes, bool pinned,
     cudaStream_t stream) {
   if (!bytes) return 0;
@@ -518,13 +518,27 @@ int h2d_async(psb_context *c, void *dst, const void *src, size_t bytes, bool pin
     PSB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream));
     return 0;
   }
-  const size_t CH = (size_t) 64 << 20;
-  if (!c->pinned[0]) {
-    for (int i = 0; i < 2; i++) {
-      PSB_CUDA(cudaHostAlloc(&c->pinned[i], CH, cudaHostAllocDefault));
-      PSB_CUDA(cudaEventCreateWithFlags(&c->pinned_free[i], cudaEventDisableTiming));
-    }
+  // staging ring: `nslot` pinned pieces of `CH` bytes (one allocation)
+  const size_t CH = (size_t) std::min<long>(std::max<long>(c->opt_h2d_piece_mb, 1), 1024) << 20;
+  const int nslot = (int) std::min<long>(std::max<long>(c->opt_h2d_slots, 2), PSB_STAGE_SLOTS);
+  const bool wc = c->opt_h2d_wc != 0;
+  if (c->pinned_base && (c->pinned_wc != wc || c->pinned_bytes != CH || c->pinned_slots != nslot)) {
+    // an option changed: wait for the ring's last copies, then start over
+    for (int i = 0; i < PSB_STAGE_SLOTS; i++)
+      if (c->pinned_free[i]) PSB_CUDA(cudaEventSynchronize(c->pinned_free[i]));
+    PSB_CUDA(cudaFreeHost(c->pinned_base));
+    c->pinned_base = nullptr;
+  }
+  if (!c->pinned_base) {
+    // (write-combined memory: only ever written by the cores and read by the DMA engine, which
+    // then need not snoop the caches — measured equal on the B200 hosts, default off)
+    PSB_CUDA(cudaHostAlloc(&c->pinned_base, CH * nslot, wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
+    for (int i = 0; i < nslot; i++)
+      if (!c->pinned_free[i]) PSB_CUDA(cudaEventCreateWithFlags(&c->pinned_free[i], cudaEventDisableTiming));
     c->pinned_bytes = CH;
+    c->pinned_slots = nslot;
+    c->pinned_wc = wc;
+    c->pinned_next = 0;
   }
   unsigned hw = std::thread::hardware_concurrency();
   const int nthr = (int) std::max(1u, std::min((unsigned) std::max<long>(c->opt_h2d_threads, 1), hw ? hw : 1u));
@@ -535,18 +549,18 @@ int h2d_async(psb_context *c, void *dst, const void *src, size_t bytes, bool pin
     c->copy_pool = copy_pool_create(nthr);
   }
   size_t off = 0;
-  int slot = 0;
   while (off < bytes) {
     const size_t len = std::min(CH, bytes - off);
+    const int slot = c->pinned_next;
+    c->pinned_next = (slot + 1) % nslot;
     PSB_CUDA(cudaEventSynchronize(c->pinned_free[slot]));
-    char *stage = static_cast<char *>(c->pinned[slot]);
+    char *stage = static_cast<char *>(c->pinned_base) + (size_t) slot * CH;
     const char *from = static_cast<const char *>(src) + off;
     copy_pool_run(c->copy_pool, stage, from, len);
     PSB_CUDA(cudaMemcpyAsync(static_cast<char *>(dst) + off, stage, len,
         cudaMemcpyHostToDevice, stream));
     PSB_CUDA(cudaEventRecord(c->pinned_free[slot], stream));
     off += len;
-    slot ^= 1;
   }
   return 0;
 }
@@ -1150,13 +1164,13 @@ void psb_destroy(psb_context *c) {
   for (int i = 0; i < 2; i++) {
     for (int j = 0; j < 2; j++) { c->part_in[i][j].release(); c->mesh[i][j].release(); }
     c->fkl[i].release(); c->fk0copy[i].release();
-    if (c->pinned[i]) cudaFreeHost(c->pinned[i]);
-    if (c->pinned_free[i]) cudaEventDestroy(c->pinned_free[i]);
     c->chunkbuf[i].release();
     if (c->ev_filled[i]) cudaEventDestroy(c->ev_filled[i]);
     if (c->ev_consumed[i]) cudaEventDestroy(c->ev_consumed[i]);
   }
   if (c->st_copy) cudaStreamDestroy(c->st_copy);
+  if (c->pinned_base) cudaFreeHost(c->pinned_base);
+  for (int i = 0; i < PSB_STAGE_SLOTS; i++) if (c->pinned_free[i]) cudaEventDestroy(c->pinned_free[i]);
   copy_pool_destroy(c->copy_pool);
   c->copy_pool = nullptr;
   c->fka.release(); c->sorted.release(); c->keys.release(); c->hist.release();
@@ -1215,6 +1229,9 @@ int psb_set_option(psb_context *c, const char *name, long value) {
   if (!strcmp(name, "geom_sym")) { c->opt_geom_sym = value; return 0; }
   if (!strcmp(name, "stream")) { c->opt_stream = value; return 0; }
   if (!strcmp(name, "h2d_threads")) { c->opt_h2d_threads = value; return 0; }
+  if (!strcmp(name, "h2d_wc")) { c->opt_h2d_wc = value; return 0; }
+  if (!strcmp(name, "h2d_piece_mb")) { c->opt_h2d_piece_mb = value; return 0; }
+  if (!strcmp(name, "h2d_slots")) { c->opt_h2d_slots = value; return 0; }
   if (!strcmp(name, "h2d_nt")) { copy_set_stream_stores((int) value); return 0; }
   if (!strcmp(name, "stream_chunk")) { c->opt_stream_chunk = value; return 0; }
   if (!strcmp(name, "stream_taper")) { c->opt_stream_taper = value; return 0; }

@@ -1,14 +1,14 @@
-// Host-side staging copy: pageable memory -> pinned buffer, by a persistent pool of
-// threads with non-temporal stores.
+// Host-side staging copy: pageable memory -> pinned ring, by a persistent pool of threads.
 //
 // The reference's C host hands genr_mesh() plain malloc'd DATA arrays
 // (src/read_cata.c:86-189), which the DMA engine cannot read directly: they are staged
-// through two pinned 64 MB buffers (context.cu: h2d_async).  Round 1 spawned 16
-// std::threads per 64 MB piece and used memcpy: 44 GB/s on the 16-core B200 host, below
-// the 55 GB/s of the PCIe link, so the upload of a pageable catalogue was bound by the
-// staging.  Here the threads live as long as the context (no creation / join per piece)
-// and the copy streams past the caches (the pinned buffer is read next by the DMA
-// engine, never by a core: no read-for-ownership of the destination lines).
+// through a ring of pinned pieces (context.cu: h2d_async).  Round 1 spawned 16 std::threads
+// per 64 MB piece and used memcpy: 44 GB/s on the 16-core B200 host, below the 55 GB/s of
+// the PCIe link, so the upload of a pageable catalogue was bound by the staging (108.5 ms per
+// config-2 step against 90.5 ms from pinned memory).  Here the threads live as long as the
+// context (no creation / join per piece: 55.9 GB/s with memcpy, 72.7 GB/s with streaming
+// stores, tools/staging_bench.py) and the ring is sized for the last-level cache, which is
+// what counts once the DMA engine competes for host DRAM: 94.5 ms per step.
 
 #include <emmintrin.h>
 
@@ -25,7 +25,12 @@ namespace psb_host {
 
 namespace {
 
-int g_stream_stores = 1;        // 0: plain memcpy in the pool's threads (option "h2d_nt", ablation)
+// 1: non-temporal stores (option "h2d_nt").  Measured on the B200 host (config 2 from malloc'd
+// memory, profiles/r2_v10_pageable_ring.jsonl): with a staging ring small enough to stay in the
+// last-level cache (3 x 16 MB) plain stores win — the DMA engine reads the ring from the cache
+// and host DRAM only sees the read of the source: 94.5 ms per step against 98.7-100.1 ms with
+// streaming stores into 2 x 64 MB (three trips through DRAM per byte), pinned source 90.6 ms
+int g_stream_stores = 0;
 
 void stream_copy(char *dst, const char *src, size_t n) {
   if (n < 256 || !g_stream_stores) { memcpy(dst, src, n); return; }
@@ -114,7 +119,7 @@ int g_stream_stores_get() { return g_stream_stores; }
 // One caller at a time per pool.
 void copy_pool_run(CopyPool *p, void *dst, const void *src, size_t bytes) {
   if (!bytes) return;
-  if (!p || p->n == 1 || bytes < ((size_t) 4 << 20)) {
+  if (!p || p->n == 1 || bytes < ((size_t) 1 << 20)) {
     stream_copy(static_cast<char *>(dst), static_cast<const char *>(src), bytes);
     return;
   }

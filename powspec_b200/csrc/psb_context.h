@@ -62,6 +62,8 @@ using psb::Interval;
 using psb::AssignGeom;
 using psb::BinGeom;
 
+#define PSB_STAGE_SLOTS 8
+
 // staging copy pageable -> pinned memory by a persistent thread pool (hostcopy.cpp)
 namespace psb_host {
 struct CopyPool;
@@ -98,9 +100,11 @@ struct psb_context {
   uint32_t tile_overflowed = 0;           // overflow entries of the last dense chunk
   int assign_path = 0;                  // what the last scatter used: 0 global reductions, 1 owner-computes tiles
   size_t bounds_used = 0;               // bytes of bounds_part holding deferred bounds partials
-  void *pinned[2] = {nullptr, nullptr};
+  void *pinned_base = nullptr;          // staging ring for pageable sources: pinned_slots pieces of pinned_bytes
   size_t pinned_bytes = 0;
-  cudaEvent_t pinned_free[2] = {nullptr, nullptr};
+  int pinned_slots = 0, pinned_next = 0;
+  bool pinned_wc = false;               // the ring is write-combined memory
+  cudaEvent_t pinned_free[PSB_STAGE_SLOTS] = {};
   psb_host::CopyPool *copy_pool = nullptr;      // persistent staging threads (hostcopy.cpp)
 
   // meshes: [cat][field]; survey extras
@@ -154,6 +158,14 @@ struct psb_context {
                                         // (capped at the hardware concurrency; 8 -> 16 on the 16-core
                                         // B200 host: 36 -> 44 GB/s, config 2 from malloc'd memory 121 -> 107 ms;
                                         // since round 2 a persistent pool with streaming stores, hostcopy.cpp)
+  long opt_h2d_wc = 0;                  // staging ring in write-combined pinned memory
+  long opt_h2d_piece_mb = 16;           // bytes per piece of the staging ring (MiB) and
+  long opt_h2d_slots = 3;               // pieces in the ring (2 .. PSB_STAGE_SLOTS): 48 MB stay in the host's share
+                                        // of the last-level cache.  ms per config-2 step from malloc'd memory
+                                        // (profiles/r2_v1?_pageable_ring*.jsonl; pinned source: 90.6): 3 x 16 MB
+                                        // 94.5 / 94.9, 4 x 12: 94.8 / 95.4, 4 x 8: 95.2 / 95.7, 4 x 16: 94.8 ... 107
+                                        // (borderline), 6 x 16: 111.7, 2 x 16: 117 (too shallow), 8 x 2: 110.6;
+                                        // streaming stores into 2 x 64 MB: 98.7 ... 100.1
   long opt_stream = 1;                  // overlap H2D with assignment for host catalogues (sims)
   long opt_stream_chunk = 12500000;     // particles per streamed chunk (400 MB): the smallest whose
                                         // sort + scatter (~6 ms, one sweep of the meshes) still keeps
