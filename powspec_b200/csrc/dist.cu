@@ -1051,6 +1051,10 @@ psb_group *psb_group_create(const int *devices, int nranks) {
     g->device.push_back(devices[r]);
     psb_context *c = psb_create(devices[r]);
     if (!c) { psb_group_destroy(g); return nullptr; }
+    // pageable catalogues: every rank stages its own share (hostcopy.cpp); the ranks share the
+    // host's cores, so each pool takes its part of them instead of 16 threads per rank
+    const unsigned hw = std::thread::hardware_concurrency();
+    c->opt_h2d_threads = std::max<long>(2, std::min<long>(c->opt_h2d_threads, (long) (hw ? hw : 16u) / nranks));
     g->ctx.push_back(c);
     psb_dist *d = dist_new(c, new LocalTransport(g->hub, r, devices[r]));
     if (!d) { psb_group_destroy(g); return nullptr; }
