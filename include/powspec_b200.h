@@ -324,7 +324,8 @@ void psb_device_free(psb_context *ctx, void *ptr);
 int psb_copy_to_host(psb_context *ctx, void *dst, const void *src_dev, size_t bytes);
 /* test hook, no GPU needed: the staging copy that carries pageable host catalogues (the
  * reference's malloc'd DATA arrays, src/read_cata.c:86-189) into the pinned upload buffers —
- * a persistent pool of `nthreads` host threads with non-temporal stores (csrc/hostcopy.cpp).
+ * a persistent pool of `nthreads` host threads (csrc/hostcopy.cpp; plain or, with option
+ * "h2d_nt", non-temporal stores).
  * Copies src to dst `repeats` times; returns the number of threads the pool was asked for */
 int psb_test_host_copy(void *dst, const void *src, size_t bytes, int nthreads, int repeats);
 /* the same, as the upload path uses it: `bytes` of src streamed through two alternating staging
